@@ -1,0 +1,1019 @@
+// C ABI of the BTF Gibbs-sweep engine (include/btf_b200.h): device-resident state,
+// sweep scheduling (eager or CUDA-graph replay), sample collection, parity hooks.
+#include "../../include/btf_b200.h"
+#include "kernels.h"
+#include "nccl_shard.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace btf;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return set_err(BTF_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct DevBuf {
+    double* p = nullptr;
+    size_t n = 0;
+};
+
+enum Phase { PH_NU2 = 0, PH_SIGMA2, PH_TAU2, PH_LAM2, PH_ROW_STATS, PH_ROW_SOLVE, PH_COL_STATS, PH_BAND_SOLVE, PH_COMM, PH_COUNT };
+
+struct btf_engine {
+    btf_config cfg;
+    int N, M, T, K, order, q, kd, RD, L, nco, P, Ppad, nloc, nloc_pad, n;
+    int Mloc;
+    int sm_count;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // state
+    double *W = nullptr, *V = nullptr, *Tau2 = nullptr, *Tau2_a = nullptr, *Tau2_b = nullptr, *Tau2_c = nullptr;
+    Scalars* scal = nullptr;
+    // data
+    uint8_t* cnt = nullptr;      // Gaussian: # observed replicates; PG paths: observed flag
+    double* S = nullptr;         // Gaussian: replicate sum; PG paths: kappa = y - n/2
+    double* ntr = nullptr;       // PG paths: number of trials b
+    double* omega = nullptr;     // PG paths: Polya-Gamma draws
+    double* Yraw = nullptr;      // NB: raw counts [nloc][P][R]
+    int nreps = 1;
+    bool has_data = false, data_reduced = false;
+    // NB dispersion
+    double* Rdisp = nullptr; int Rn = 1, Rm = 1, Rt = 1; double* nb_work = nullptr;
+    // penalty
+    std::vector<double> delta;   // dense [RD][T]
+    int *d_start = nullptr, *d_width = nullptr; double* d_coef = nullptr; int d_maxw = 0;
+    int *pm_ptr = nullptr, *pm_row = nullptr; double* pm_coef = nullptr;
+    // statistics
+    StatsPlan plan_row, plan_col;
+    double *row_stats = nullptr, *col_stats = nullptr;
+    // workspaces
+    double *work_L = nullptr, *work_y = nullptr, *partials = nullptr, *lam_partials = nullptr, *resid_partials = nullptr;
+    size_t partials_n = 0;
+    // snapshots for async sample collection
+    double *snapW = nullptr, *snapV = nullptr, *snapTau2 = nullptr, *snapScal = nullptr, *snapR = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    double* pinned_scal = nullptr;
+    // parity hooks
+    std::map<std::string, DevBuf> inject;
+    bool diag = false;
+    std::map<std::string, DevBuf> diagbuf;
+    int* diag_retries = nullptr;
+    // scheduling
+    bool resid_valid = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_launches = 0;
+    int64_t launches = 0;
+    // phase timing
+    bool time_phases = false;
+    cudaEvent_t ph_ev[PH_COUNT + 1] = {nullptr};
+    double ph_ms[PH_COUNT] = {0};
+    // multi GPU
+    NcclShard* shard = nullptr;
+};
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+void btf_config_default(btf_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->nembeds = 5; c->tf_order = 2;
+    c->sigma2_a = c->sigma2_b = 0.1; c->nu2_a = c->nu2_b = 0.1;
+    c->stability = 1e-6;
+    c->force_psd = 1; c->force_psd_eps = 1e-6; c->force_psd_attempts = 4;
+    c->ref_compat_lam2 = 1;
+    c->sample_mask = BTF_SAMPLE_ALL;
+    c->seed = 42;
+    c->nmetropolis = 30; c->rpropstdev = 0.1; c->rstdev = 1.0; c->rdims_mask = 7;
+    c->world_size = 1;
+    c->use_graph = 1;
+}
+
+const char* btf_last_error(void) { return g_err; }
+
+// ---- trend-filtering penalty (utils.py:56-98), dense on the host
+static std::vector<double> build_delta(int T, int order, int* RD_out) {
+    auto matmul = [](const std::vector<double>& A, int ar, int ac, const std::vector<double>& B, int bc) {
+        std::vector<double> C((size_t)ar * bc, 0.0);
+        for (int i = 0; i < ar; ++i)
+            for (int k = 0; k < ac; ++k) {
+                double a = A[(size_t)i * ac + k];
+                if (a == 0.0) continue;
+                for (int j = 0; j < bc; ++j) C[(size_t)i * bc + j] += a * B[(size_t)k * bc + j];
+            }
+        return C;
+    };
+    std::vector<double> D((size_t)(T - 1) * T, 0.0), Dt((size_t)T * (T - 1), 0.0);
+    for (int i = 0; i < T - 1; ++i) {
+        D[(size_t)i * T + i] = -1.0; D[(size_t)i * T + i + 1] = 1.0;
+        Dt[(size_t)i * (T - 1) + i] = -1.0; Dt[(size_t)(i + 1) * (T - 1) + i] = 1.0;
+    }
+    std::vector<double> out(T, 0.0);
+    out[0] = 1.0;   // anchor row e_0
+    int rows = 1;
+    for (int k = 0; k <= order; ++k) {
+        std::vector<double> cur = D;
+        int cr = T - 1;
+        for (int i = 0; i < k; ++i) {
+            if (i % 2 == 0) { cur = matmul(Dt, T, T - 1, cur, T); cr = T; }
+            else { cur = matmul(D, T - 1, T, cur, T); cr = T - 1; }
+        }
+        out.insert(out.end(), cur.begin(), cur.end());
+        rows += cr;
+    }
+    *RD_out = rows;
+    return out;
+}
+
+template <typename Tp>
+static cudaError_t dev_alloc(Tp** p, size_t n, bool zero = true) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp));
+    if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+    return e;
+}
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int btf_create(const btf_config* c, btf_engine** out) {
+    if (!c || !out) return set_err(BTF_EINVAL, "null argument");
+    if (c->nrows < 1 || c->ncols < 1 || c->ndepth < 2) return set_err(BTF_EINVAL, "bad shape");
+    if (c->nembeds < 1 || c->nembeds > 32) return set_err(BTF_EINVAL, "nembeds must be in [1, 32]");
+    if (c->tf_order < 0 || c->tf_order > 3) return set_err(BTF_EINVAL, "tf_order must be in [0, 3]");
+    if (c->ndepth < c->tf_order + 2) return set_err(BTF_EINVAL, "ndepth must be >= tf_order + 2");
+    btf_engine* e = new btf_engine();
+    e->cfg = *c;
+    if (e->cfg.world_size <= 1) {
+        e->cfg.world_size = 1; e->cfg.rank = 0;
+        e->cfg.row_begin = 0; e->cfg.row_end = c->nrows; e->cfg.col_begin = 0; e->cfg.col_end = c->ncols;
+    }
+    e->N = c->nrows; e->M = c->ncols; e->T = c->ndepth; e->K = c->nembeds; e->order = c->tf_order;
+    e->q = e->order + 1; e->kd = e->q * e->K; e->n = e->T * e->K;
+    e->L = e->K * (e->K + 1) / 2; e->nco = e->L + e->K;
+    e->P = e->M * e->T; e->Ppad = round_up(e->P, 256);
+    e->nloc = e->cfg.row_end - e->cfg.row_begin;
+    e->nloc_pad = round_up(std::max(e->nloc, 1), 128);
+    e->Mloc = e->cfg.col_end - e->cfg.col_begin;
+    if (e->nloc < 0 || e->Mloc < 0) { delete e; return set_err(BTF_EINVAL, "bad shard"); }
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
+    for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&e->ph_ev[i]));
+
+    e->delta = build_delta(e->T, e->order, &e->RD);
+    const int RD = e->RD, T = e->T, q = e->q;
+    // stencils
+    std::vector<int> hs(RD), hw(RD);
+    int maxw = 1;
+    for (int r = 0; r < RD; ++r) {
+        int a = -1, b = -1;
+        for (int t = 0; t < T; ++t) if (e->delta[(size_t)r * T + t] != 0.0) { if (a < 0) a = t; b = t; }
+        hs[r] = a < 0 ? 0 : a; hw[r] = a < 0 ? 0 : b - a + 1;
+        maxw = std::max(maxw, hw[r]);
+    }
+    e->d_maxw = maxw;
+    std::vector<double> hc((size_t)RD * maxw, 0.0);
+    for (int r = 0; r < RD; ++r)
+        for (int x = 0; x < hw[r]; ++x) hc[(size_t)r * maxw + x] = e->delta[(size_t)r * T + hs[r] + x];
+    // CSR of the band of Delta^T diag(.) Delta : entry (t, m) -> P[t+m, t]
+    std::vector<int> pp(1, 0), pr;
+    std::vector<double> pc;
+    for (int t = 0; t < T; ++t)
+        for (int m = 0; m <= q; ++m) {
+            if (t + m < T)
+                for (int r = 0; r < RD; ++r) {
+                    double a = e->delta[(size_t)r * T + t], b = e->delta[(size_t)r * T + t + m];
+                    if (a != 0.0 && b != 0.0) { pr.push_back(r); pc.push_back(a * b); }
+                }
+            pp.push_back((int)pr.size());
+        }
+    CK(dev_alloc(&e->d_start, RD)); CK(dev_alloc(&e->d_width, RD)); CK(dev_alloc(&e->d_coef, hc.size()));
+    CK(dev_alloc(&e->pm_ptr, pp.size())); CK(dev_alloc(&e->pm_row, pr.size())); CK(dev_alloc(&e->pm_coef, pc.size()));
+    CK(cudaMemcpy(e->d_start, hs.data(), RD * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_width, hw.data(), RD * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_coef, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->pm_ptr, pp.data(), pp.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!pr.empty()) {
+        CK(cudaMemcpy(e->pm_row, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->pm_coef, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+
+    // state (W and V padded with zero rows so the statistics tiles may over-read)
+    const size_t Wn = ((size_t)round_up(e->N, 128) + 256) * e->K;
+    CK(dev_alloc(&e->W, Wn));
+    CK(dev_alloc(&e->V, (size_t)e->Ppad * e->K + 64));
+    const size_t tn = (size_t)e->M * RD;
+    CK(dev_alloc(&e->Tau2, tn)); CK(dev_alloc(&e->Tau2_a, tn)); CK(dev_alloc(&e->Tau2_b, tn)); CK(dev_alloc(&e->Tau2_c, tn));
+    CK(dev_alloc(&e->scal, 1));
+    Scalars h;
+    memset(&h, 0, sizeof(h));
+    h.nu2 = 1.0; h.sigma2 = 1.0; h.lam2 = 1.0; h.lam2_a = 1.0;
+    CK(cudaMemcpy(e->scal, &h, sizeof(h), cudaMemcpyHostToDevice));
+    // one-time fills so a forgotten set_state cannot divide by zero
+    {
+        std::vector<double> ones(tn, 1.0);
+        for (double* p : {e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c})
+            CK(cudaMemcpy(p, ones.data(), tn * sizeof(double), cudaMemcpyHostToDevice));
+    }
+
+    // data
+    const size_t cells = (size_t)e->nloc_pad * e->Ppad;
+    CK(dev_alloc(&e->cnt, cells));
+    CK(dev_alloc(&e->S, cells));
+    const bool pg = c->likelihood != BTF_GAUSSIAN;
+    if (pg) { CK(dev_alloc(&e->ntr, cells)); CK(dev_alloc(&e->omega, cells)); }
+    if (c->likelihood == BTF_NEGBINOMIAL) {
+        e->Rn = (c->rdims_mask & 1) ? 1 : e->N;
+        e->Rm = (c->rdims_mask & 2) ? 1 : e->M;
+        e->Rt = (c->rdims_mask & 4) ? 1 : e->T;
+        CK(dev_alloc(&e->Rdisp, (size_t)e->Rn * e->Rm * e->Rt));
+    }
+
+    // statistics plans and buffers
+    if (!plan_stats(&e->plan_row, e->K, false, pg, e->nloc_pad, e->Ppad, e->nloc, c->stats_splits_row, e->sm_count))
+        { delete e; return set_err(BTF_EINVAL, "no row-statistics plan for K=%d", c->nembeds); }
+    if (!plan_stats(&e->plan_col, e->K, true, pg, e->Ppad, e->nloc_pad, e->P, c->stats_splits_col, e->sm_count))
+        { delete e; return set_err(BTF_EINVAL, "no column-statistics plan for K=%d", c->nembeds); }
+    CK(dev_alloc(&e->row_stats, e->plan_row.nsplit * e->plan_row.out_elems_per_split));
+    CK(dev_alloc(&e->col_stats, e->plan_col.nsplit * e->plan_col.out_elems_per_split));
+
+    // workspaces
+    CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->n * (e->kd + 1)));
+    CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->n));
+    e->partials_n = std::max<size_t>((size_t)(e->Ppad / 256) * (e->nloc_pad / 64), (size_t)2 * 148 * 16) + 64;
+    CK(dev_alloc(&e->partials, e->partials_n));
+    CK(dev_alloc(&e->lam_partials, e->M));
+    CK(dev_alloc(&e->resid_partials, e->M));
+    CK(dev_alloc(&e->snapW, (size_t)e->N * e->K));
+    CK(dev_alloc(&e->snapV, (size_t)e->P * e->K));
+    CK(dev_alloc(&e->snapTau2, tn));
+    CK(dev_alloc(&e->snapScal, 8));
+    if (e->Rdisp) CK(dev_alloc(&e->snapR, (size_t)e->Rn * e->Rm * e->Rt));
+    CK(cudaMallocHost((void**)&e->pinned_scal, 64 * sizeof(double)));
+    CK(dev_alloc(&e->diag_retries, std::max(e->Mloc, 1)));
+    *out = e;
+    return BTF_OK;
+}
+
+static void free_graph(btf_engine* e) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+}
+
+void btf_destroy(btf_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    free_graph(e);
+    if (e->shard) nccl_shard_destroy(e->shard);
+    void* ptrs[] = {e->W, e->V, e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c, e->scal, e->cnt, e->S, e->ntr, e->omega,
+                    e->Yraw, e->Rdisp, e->nb_work, e->d_start, e->d_width, e->d_coef, e->pm_ptr, e->pm_row, e->pm_coef,
+                    e->row_stats, e->col_stats, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
+                    e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& kv : e->diagbuf) if (kv.second.p) cudaFree(kv.second.p);
+    if (e->pinned_scal) cudaFreeHost(e->pinned_scal);
+    if (e->ev_snap) cudaEventDestroy(e->ev_snap);
+    if (e->ev_copied) cudaEventDestroy(e->ev_copied);
+    for (int i = 0; i <= PH_COUNT; ++i) if (e->ph_ev[i]) cudaEventDestroy(e->ph_ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+int btf_delta_rows(const btf_engine* e) { return e ? e->RD : 0; }
+int btf_set_sample_mask(btf_engine* e, int32_t mask) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    if (mask != e->cfg.sample_mask) {
+        cudaStreamSynchronize(e->stream);
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        e->cfg.sample_mask = mask;
+        e->resid_valid = false;
+    }
+    return BTF_OK;
+}
+int64_t btf_kernel_launches(const btf_engine* e) { return e ? e->launches : 0; }
+
+// ------------------------------------------------------------------ data
+static int upload_rows(btf_engine* e, const double* src, size_t row_elems, int row0, int rows, double* staging) {
+    // src is a host pointer to the first of `rows` rows of row_elems doubles
+    CK(cudaMemcpyAsync(staging, src + (size_t)row0 * row_elems, (size_t)rows * row_elems * sizeof(double),
+                       cudaMemcpyHostToDevice, e->stream));
+    return BTF_OK;
+}
+
+int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps) {
+    if (!e || !Y || nreps < 1 || nreps > 255) return set_err(BTF_EINVAL, "bad arguments (1 <= nreps <= 255)");
+    if (e->cfg.likelihood != BTF_GAUSSIAN) return set_err(BTF_ESTATE, "engine is not Gaussian");
+    CK(cudaSetDevice(e->cfg.device));
+    free_graph(e);
+    e->nreps = nreps;
+    const size_t row_elems = (size_t)e->P * nreps;
+    CK(cudaMemsetAsync(&e->scal->ss_total, 0, 2 * sizeof(double), e->stream));   // ss_total, n_obs
+    const bool on_dev = is_device_ptr(Y);
+    double* staging = nullptr;
+    int chunk = e->nloc;
+    if (!on_dev) {
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->nloc, ((size_t)256 << 20) / (row_elems * 8)));
+        CK(cudaMalloc((void**)&staging, (size_t)chunk * row_elems * sizeof(double)));
+    }
+    for (int r0 = 0; r0 < e->nloc; r0 += chunk) {
+        int rows = std::min(chunk, e->nloc - r0);
+        const double* src = on_dev ? Y + (size_t)r0 * row_elems : staging;
+        if (!on_dev) { int rc = upload_rows(e, Y, row_elems, r0, rows, staging); if (rc) return rc; }
+        int nb = 0;
+        launch_prereduce_gaussian(src, rows, e->P, nreps, e->cnt + (size_t)r0 * e->Ppad, e->S + (size_t)r0 * e->Ppad,
+                                  e->Ppad, e->partials, &nb, e->stream);
+        launch_reduce_add(e->partials, nb, 2, &e->scal->ss_total, e->stream);
+        launch_reduce_add(e->partials + 1, nb, 2, &e->scal->n_obs, e->stream);
+        e->launches += 3;
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    if (staging) CK(cudaFree(staging));
+    CK(cudaGetLastError());
+    e->has_data = true; e->data_reduced = false; e->resid_valid = false;
+    return BTF_OK;
+}
+
+int btf_set_data_binomial(btf_engine* e, const double* Ys, const double* Nt) {
+    if (!e || !Ys || !Nt) return set_err(BTF_EINVAL, "null argument");
+    if (e->cfg.likelihood != BTF_BINOMIAL) return set_err(BTF_ESTATE, "engine is not Binomial");
+    CK(cudaSetDevice(e->cfg.device));
+    free_graph(e);
+    const size_t row_elems = (size_t)e->P;
+    const bool on_dev = is_device_ptr(Ys) && is_device_ptr(Nt);
+    double *sy = nullptr, *sn = nullptr;
+    int chunk = e->nloc;
+    if (!on_dev) {
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->nloc, ((size_t)128 << 20) / (row_elems * 8)));
+        CK(cudaMalloc((void**)&sy, (size_t)chunk * row_elems * sizeof(double)));
+        CK(cudaMalloc((void**)&sn, (size_t)chunk * row_elems * sizeof(double)));
+    }
+    for (int r0 = 0; r0 < e->nloc; r0 += chunk) {
+        int rows = std::min(chunk, e->nloc - r0);
+        const double *py = Ys + (size_t)r0 * row_elems, *pn = Nt + (size_t)r0 * row_elems;
+        if (!on_dev) {
+            int rc = upload_rows(e, Ys, row_elems, r0, rows, sy); if (rc) return rc;
+            rc = upload_rows(e, Nt, row_elems, r0, rows, sn); if (rc) return rc;
+            py = sy; pn = sn;
+        }
+        launch_prereduce_binomial(py, pn, rows, e->P, e->cnt + (size_t)r0 * e->Ppad, e->S + (size_t)r0 * e->Ppad,
+                                  e->ntr + (size_t)r0 * e->Ppad, e->Ppad, e->stream);
+        e->launches += 1;
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    if (sy) CK(cudaFree(sy));
+    if (sn) CK(cudaFree(sn));
+    CK(cudaGetLastError());
+    e->has_data = true; e->data_reduced = true;
+    return BTF_OK;
+}
+
+int btf_set_data_negbin(btf_engine* e, const double* Y, int32_t nreps) {
+    if (!e || !Y || nreps < 1) return set_err(BTF_EINVAL, "bad arguments");
+    if (e->cfg.likelihood != BTF_NEGBINOMIAL) return set_err(BTF_ESTATE, "engine is not NegativeBinomial");
+    if (e->cfg.world_size > 1) return set_err(BTF_EINVAL, "negative-binomial path is single-GPU");
+    CK(cudaSetDevice(e->cfg.device));
+    free_graph(e);
+    e->nreps = nreps;
+    const size_t total = (size_t)e->nloc * e->P * nreps;
+    if (e->Yraw) { CK(cudaFree(e->Yraw)); e->Yraw = nullptr; }
+    CK(cudaMalloc((void**)&e->Yraw, total * sizeof(double)));
+    CK(cudaMemcpy(e->Yraw, Y, total * sizeof(double), is_device_ptr(Y) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    if (e->nb_work) { CK(cudaFree(e->nb_work)); e->nb_work = nullptr; }
+    const size_t rsize = (size_t)e->Rn * e->Rm * e->Rt;
+    CK(dev_alloc(&e->nb_work, 8 * rsize + 64));
+    e->has_data = true; e->data_reduced = true;
+    return BTF_OK;
+}
+
+// ------------------------------------------------------------------ state
+struct StateRef { double* p; size_t n; bool scalar_field; };
+
+static bool state_ref(btf_engine* e, const std::string& nm, StateRef* r) {
+    const size_t tn = (size_t)e->M * e->RD;
+    r->scalar_field = false;
+    if (nm == "W") { r->p = e->W; r->n = (size_t)e->N * e->K; return true; }
+    if (nm == "V") { r->p = e->V; r->n = (size_t)e->P * e->K; return true; }
+    if (nm == "Tau2") { r->p = e->Tau2; r->n = tn; return true; }
+    if (nm == "Tau2_a") { r->p = e->Tau2_a; r->n = tn; return true; }
+    if (nm == "Tau2_b") { r->p = e->Tau2_b; r->n = tn; return true; }
+    if (nm == "Tau2_c") { r->p = e->Tau2_c; r->n = tn; return true; }
+    if (nm == "R" && e->Rdisp) { r->p = e->Rdisp; r->n = (size_t)e->Rn * e->Rm * e->Rt; return true; }
+    r->scalar_field = true; r->n = 1;
+    if (nm == "nu2") { r->p = &e->scal->nu2; return true; }
+    if (nm == "sigma2") { r->p = &e->scal->sigma2; return true; }
+    if (nm == "lam2") { r->p = &e->scal->lam2; return true; }
+    if (nm == "lam2_a") { r->p = &e->scal->lam2_a; return true; }
+    if (nm == "resid") { r->p = &e->scal->resid; return true; }
+    if (nm == "ss_total") { r->p = &e->scal->ss_total; return true; }
+    if (nm == "n_obs") { r->p = &e->scal->n_obs; return true; }
+    return false;
+}
+
+// pitched [nloc][P] <-> dense copies for omega / Ntrials
+static int copy_pitched(btf_engine* e, double* dev, double* host, bool to_host) {
+    if (to_host)
+        CK(cudaMemcpy2D(host, (size_t)e->P * 8, dev, (size_t)e->Ppad * 8, (size_t)e->P * 8, e->nloc, cudaMemcpyDeviceToHost));
+    else
+        CK(cudaMemcpy2D(dev, (size_t)e->Ppad * 8, host, (size_t)e->P * 8, (size_t)e->P * 8, e->nloc, cudaMemcpyHostToDevice));
+    return BTF_OK;
+}
+
+int btf_set_state(btf_engine* e, const char* name, const double* host, size_t n) {
+    if (!e || !name || !host) return set_err(BTF_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    std::string nm(name);
+    if ((nm == "omega" && e->omega) || (nm == "Ntrials" && e->ntr)) {
+        if (n != (size_t)e->nloc * e->P) return set_err(BTF_EINVAL, "%s: expected %zu values", name, (size_t)e->nloc * e->P);
+        return copy_pitched(e, nm == "omega" ? e->omega : e->ntr, const_cast<double*>(host), false);
+    }
+    StateRef r;
+    if (!state_ref(e, nm, &r)) return set_err(BTF_EINVAL, "unknown state '%s'", name);
+    if (n != r.n) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, r.n, n);
+    CK(cudaMemcpy(r.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (nm == "W" || nm == "V") e->resid_valid = false;
+    return BTF_OK;
+}
+
+int btf_get_state(btf_engine* e, const char* name, double* host, size_t n) {
+    if (!e || !name || !host) return set_err(BTF_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    std::string nm(name);
+    if (nm == "Delta") {
+        if (n != e->delta.size()) return set_err(BTF_EINVAL, "Delta: expected %zu values", e->delta.size());
+        memcpy(host, e->delta.data(), n * sizeof(double));
+        return BTF_OK;
+    }
+    if ((nm == "omega" && e->omega) || (nm == "Ntrials" && e->ntr) || (nm == "kappa" && e->S)) {
+        if (n != (size_t)e->nloc * e->P) return set_err(BTF_EINVAL, "%s: expected %zu values", name, (size_t)e->nloc * e->P);
+        return copy_pitched(e, nm == "omega" ? e->omega : (nm == "kappa" ? e->S : e->ntr), host, true);
+    }
+    StateRef r;
+    if (!state_ref(e, nm, &r)) return set_err(BTF_EINVAL, "unknown state '%s'", name);
+    if (n != r.n) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, r.n, n);
+    CK(cudaMemcpy(host, r.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return BTF_OK;
+}
+
+// ------------------------------------------------------------------ parity hooks
+int btf_inject_noise(btf_engine* e, const char* name, const double* host, size_t n) {
+    if (!e || !name || !host) return set_err(BTF_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    std::string nm(name);
+    size_t want = 0;
+    const size_t rsize = (size_t)e->Rn * e->Rm * e->Rt;
+    if (nm == "z_W") want = (size_t)e->N * e->K;
+    else if (nm == "z_V") want = (size_t)e->P * e->K;
+    else if (nm == "g_tau") want = (size_t)e->M * 4 * e->RD;
+    else if (nm == "g_lam") want = 2;
+    else if (nm == "g_sigma2" || nm == "g_nu2") want = 1;
+    else if (nm == "omega") want = (size_t)e->nloc * e->P;
+    else if (nm == "z_R" || nm == "u_R") want = (size_t)e->cfg.nmetropolis * rsize;
+    else return set_err(BTF_EINVAL, "unknown noise '%s'", name);
+    if (n != want) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, want, n);
+    DevBuf& b = e->inject[nm];
+    if (b.p && b.n != n) { cudaFree(b.p); b.p = nullptr; }
+    if (!b.p) { CK(cudaMalloc((void**)&b.p, n * sizeof(double))); b.n = n; }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(b.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
+    return BTF_OK;
+}
+
+static const double* inj(btf_engine* e, const char* nm) {
+    auto it = e->inject.find(nm);
+    return it == e->inject.end() ? nullptr : it->second.p;
+}
+
+static void clear_inject(btf_engine* e) {
+    for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
+    e->inject.clear();
+}
+
+static double* diag_get(btf_engine* e, const char* nm, size_t n) {
+    if (!e->diag) return nullptr;
+    DevBuf& b = e->diagbuf[nm];
+    if (!b.p || b.n != n) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        if (cudaMalloc((void**)&b.p, std::max<size_t>(n, 1) * sizeof(double)) != cudaSuccess) { b.p = nullptr; return nullptr; }
+        b.n = n;
+    }
+    cudaMemsetAsync(b.p, 0, n * sizeof(double), e->stream);
+    return b.p;
+}
+
+int btf_enable_diag(btf_engine* e, int32_t on) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    e->diag = on != 0;
+    if (!e->diag) {
+        for (auto& kv : e->diagbuf) if (kv.second.p) cudaFree(kv.second.p);
+        e->diagbuf.clear();
+    }
+    return BTF_OK;
+}
+
+int btf_get_diag(btf_engine* e, const char* name, double* host, size_t n) {
+    if (!e || !name || !host) return set_err(BTF_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    std::string nm(name);
+    if (nm == "nu2_rate" || nm == "lam2_rate" || nm == "info") {
+        Scalars h;
+        CK(cudaMemcpy(&h, e->scal, sizeof(h), cudaMemcpyDeviceToHost));
+        if (nm == "nu2_rate") { if (n != 3) return set_err(BTF_EINVAL, "nu2_rate: 3 values"); host[0] = h.nu2_a_post; host[1] = h.nu2_b_post; host[2] = h.n_obs; }
+        else if (nm == "lam2_rate") { if (n != 2) return set_err(BTF_EINVAL, "lam2_rate: 2 values"); host[0] = h.lam2_rate; host[1] = h.lam2_shape; }
+        else { if (n != 3) return set_err(BTF_EINVAL, "info: 3 values"); host[0] = h.info_w; host[1] = h.info_v; host[2] = h.retries_v; }
+        return BTF_OK;
+    }
+    if (nm == "row_stats" || nm == "col_stats") {
+        // sum of the split partials, in split order
+        const StatsPlan& pl = nm == "row_stats" ? e->plan_row : e->plan_col;
+        const double* src = nm == "row_stats" ? e->row_stats : e->col_stats;
+        if (n != pl.out_elems_per_split) return set_err(BTF_EINVAL, "%s: expected %zu values", name, pl.out_elems_per_split);
+        std::vector<double> tmp(n);
+        std::fill(host, host + n, 0.0);
+        for (int s = 0; s < pl.nsplit; ++s) {
+            CK(cudaMemcpy(tmp.data(), src + (size_t)s * n, n * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) host[i] += tmp[i];
+        }
+        return BTF_OK;
+    }
+    if (nm == "V_retries") {
+        if (n != (size_t)e->Mloc) return set_err(BTF_EINVAL, "V_retries: expected %d values", e->Mloc);
+        std::vector<int> tmp(e->Mloc);
+        CK(cudaMemcpy(tmp.data(), e->diag_retries, e->Mloc * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < e->Mloc; ++i) host[i] = tmp[i];
+        return BTF_OK;
+    }
+    auto it = e->diagbuf.find(nm);
+    if (it == e->diagbuf.end() || !it->second.p) return set_err(BTF_ESTATE, "diagnostic '%s' not recorded (btf_enable_diag before the sweep)", name);
+    if (n != it->second.n) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, it->second.n, n);
+    CK(cudaMemcpy(host, it->second.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return BTF_OK;
+}
+
+// ------------------------------------------------------------------ the sweep
+static inline void phase_mark(btf_engine* e, int idx) {
+    if (e->time_phases) cudaEventRecord(e->ph_ev[idx], e->stream);
+}
+
+static int ensure_data_reduced(btf_engine* e) {
+    if (e->data_reduced) return BTF_OK;
+    if (e->shard) {
+        int rc = nccl_allreduce_sum(e->shard, &e->scal->ss_total, 2, e->stream);   // ss_total, n_obs adjacent
+        if (rc) return set_err(BTF_ENCCL, "all-reduce of data totals failed");
+    }
+    e->data_reduced = true;
+    return BTF_OK;
+}
+
+// Enqueue one resample(data) on e->stream.  Order: factor.py:306-311 (nu2 / omega),
+// then 112-128 (sigma2, Tau2, lam2, W, V); NB adds the R update first (494-511).
+static int enqueue_sweep(btf_engine* e) {
+    const btf_config& c = e->cfg;
+    cudaStream_t st = e->stream;
+    const bool gauss = c.likelihood == BTF_GAUSSIAN;
+    const int mask = c.sample_mask;
+    launch_bump_sweep(e->scal, st); e->launches++;
+    phase_mark(e, PH_NU2);
+
+    if (c.likelihood == BTF_NEGBINOMIAL) {
+        NbArgs nb;
+        nb.Yraw = e->Yraw; nb.nloc = e->nloc; nb.P = e->P; nb.R = e->nreps; nb.M = e->M; nb.T = e->T; nb.K = e->K;
+        nb.row_begin = c.row_begin; nb.nrows_global = e->N; nb.ld = e->Ppad;
+        nb.W = e->W + (size_t)c.row_begin * e->K; nb.V = e->V; nb.Rdisp = e->Rdisp; nb.Rn = e->Rn; nb.Rm = e->Rm; nb.Rt = e->Rt;
+        nb.nmh = (mask & BTF_SAMPLE_R) ? c.nmetropolis : 0; nb.rpropstdev = c.rpropstdev; nb.rstdev = c.rstdev;
+        nb.z_inject = inj(e, "z_R"); nb.u_inject = inj(e, "u_R");
+        nb.scal = e->scal; nb.seed = c.seed; nb.work = e->nb_work;
+        nb.obs = e->cnt; nb.kappa = e->S; nb.ntr = e->ntr;
+        launch_nb_update(nb, st); e->launches += nb.nmh > 0 ? 2 * nb.nmh + 4 : 1;
+    }
+    if (gauss) {
+        if (mask & BTF_SAMPLE_NU2) {
+            if (!e->resid_valid || c.resid_direct) {
+                int nb = 0;
+                launch_residual(e->cnt, e->S, e->Ppad, e->W + (size_t)c.row_begin * e->K, e->V, e->nloc_pad, e->Ppad,
+                                e->K, e->partials, &nb, st);
+                launch_set_resid(e->scal, e->partials, nb, st);
+                e->launches += 2;
+                if (e->shard) {
+                    // resid = ss_total + sum(partials) on every rank: combine the partial sums only
+                    if (nccl_allreduce_resid(e->shard, e->scal, st)) return set_err(BTF_ENCCL, "all-reduce(resid) failed");
+                }
+            }
+            ScalarStepArgs sa{e->scal, c.seed, c.nu2_a, c.nu2_b, inj(e, "g_nu2")};
+            launch_nu2(sa, st); e->launches++;
+        }
+    } else {
+        const double* om = inj(e, "omega");
+        if (om) {
+            cudaMemcpy2DAsync(e->omega, (size_t)e->Ppad * 8, om, (size_t)e->P * 8, (size_t)e->P * 8, e->nloc,
+                              cudaMemcpyDeviceToDevice, st);
+        } else {
+            PgArgs pa;
+            pa.obs = e->cnt; pa.ntr = e->ntr; pa.omega = e->omega; pa.ld = e->Ppad;
+            pa.W = e->W + (size_t)c.row_begin * e->K; pa.V = e->V;
+            pa.nloc = e->nloc; pa.nrows_pad = e->nloc_pad; pa.P = e->P; pa.Ppad = e->Ppad; pa.K = e->K; pa.row_begin = c.row_begin;
+            pa.scal = e->scal; pa.seed = c.seed;
+            launch_pg_draw(pa, st); e->launches++;
+        }
+    }
+    phase_mark(e, PH_SIGMA2);
+    if (mask & BTF_SAMPLE_SIGMA2) {
+        launch_w_sumsq(e->W, e->N, e->K, e->scal, st);
+        ScalarStepArgs sa{e->scal, c.seed, c.sigma2_a, c.sigma2_b, inj(e, "g_sigma2")};
+        const double nfree = e->N >= e->K ? (double)e->L + (double)(e->N - e->K) * e->K : 0.5 * e->N * (e->N + 1.0);
+        launch_sigma2(sa, nfree, st);
+        e->launches += 2;
+    }
+    phase_mark(e, PH_TAU2);
+    HyperArgs ha;
+    ha.scal = e->scal; ha.V = e->V; ha.M = e->M; ha.T = e->T; ha.K = e->K; ha.RD = e->RD;
+    ha.d_start = e->d_start; ha.d_width = e->d_width; ha.d_coef = e->d_coef; ha.d_maxw = e->d_maxw;
+    ha.Tau2 = e->Tau2; ha.Tau2_a = e->Tau2_a; ha.Tau2_b = e->Tau2_b; ha.Tau2_c = e->Tau2_c;
+    ha.stability = c.stability; ha.g_inject = inj(e, "g_tau"); ha.seed = c.seed;
+    ha.lam_partials = nullptr; ha.col_begin = 0; ha.col_end = e->M;   // replicated on every rank (Philox is keyed by (j, r))
+    if (mask & BTF_SAMPLE_TAU2) { launch_tau2(ha, st); e->launches++; }
+    phase_mark(e, PH_LAM2);
+    if (mask & BTF_SAMPLE_LAM2) {
+        HyperArgs hl = ha;
+        hl.Tau2_a = nullptr; hl.lam_partials = e->lam_partials;
+        if (c.ref_compat_lam2) { hl.col_begin = e->M - 1; hl.col_end = e->M; }
+        launch_tau2(hl, st);
+        ScalarStepArgs sa{e->scal, c.seed, 0.0, 0.0, inj(e, "g_lam")};
+        const double shape = 0.5 * ((double)e->RD * e->M * e->K + 1.0);
+        launch_lam2(sa, e->lam_partials, e->M, c.ref_compat_lam2, shape, st);
+        e->launches += 2;
+    }
+    // ---- W | rest
+    phase_mark(e, PH_ROW_STATS);
+    const void* wt = gauss ? (const void*)e->cnt : (const void*)e->omega;
+    if ((mask & BTF_SAMPLE_W) && e->nloc > 0) {
+        launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->nloc, e->row_stats, st);
+        e->launches++;
+        phase_mark(e, PH_ROW_SOLVE);
+        RowSolveArgs ra;
+        ra.stats = e->row_stats; ra.nsplit = e->plan_row.nsplit; ra.split_stride = e->plan_row.out_elems_per_split;
+        ra.nloc = e->nloc; ra.row_begin = c.row_begin; ra.K = e->K;
+        ra.scale_from_nu2 = gauss ? &e->scal->nu2 : nullptr; ra.scal = e->scal; ra.W = e->W;
+        ra.z_inject = inj(e, "z_W"); ra.seed = c.seed;
+        ra.diag_Q = diag_get(e, "W_Q", (size_t)e->N * e->K * e->K);
+        ra.diag_L = diag_get(e, "W_L", (size_t)e->N * e->K * e->K);
+        ra.diag_mean = diag_get(e, "W_mean", (size_t)e->N * e->K);
+        ra.diag_b = diag_get(e, "W_b", (size_t)e->N * e->K);
+        launch_row_solve(ra, nullptr, st); e->launches++;
+        e->resid_valid = false;
+    } else {
+        phase_mark(e, PH_ROW_SOLVE);
+    }
+    phase_mark(e, PH_COL_STATS);
+    if (e->shard && (mask & BTF_SAMPLE_W)) {
+        if (nccl_allgather_rows(e->shard, e->W, e->K, st)) return set_err(BTF_ENCCL, "all-gather(W) failed");
+    }
+    // ---- V | rest
+    if (mask & BTF_SAMPLE_V) {
+        launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->Ppad, e->P, e->col_stats, st);
+        e->launches++;
+        int nsplit = e->plan_col.nsplit;
+        if (e->shard) {
+            // sum the split partials locally is folded into the band kernel only on one GPU; across GPUs the
+            // partial statistics are first collapsed over splits, then reduce-scattered by column block
+            if (nccl_reduce_col_stats(e->shard, e->col_stats, nsplit, e->plan_col.out_elems_per_split, e->T * e->nco, st))
+                return set_err(BTF_ENCCL, "reduce-scatter(col stats) failed");
+            nsplit = 1;
+        }
+        phase_mark(e, PH_BAND_SOLVE);
+        if (e->Mloc > 0) {
+            BandSolveArgs ba;
+            ba.stats = e->col_stats; ba.nsplit = nsplit; ba.split_stride = e->plan_col.out_elems_per_split;
+            ba.col_begin = c.col_begin; ba.ncols_loc = e->Mloc; ba.T = e->T; ba.K = e->K; ba.order = e->order; ba.RD = e->RD;
+            ba.homoskedastic = gauss ? 1 : 0; ba.scal = e->scal; ba.Tau2 = e->Tau2;
+            ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
+            ba.V = e->V; ba.z_inject = inj(e, "z_V"); ba.seed = c.seed;
+            ba.work_L = e->work_L; ba.work_y = e->work_y;
+            ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
+            const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
+            ba.diag_band = diag_get(e, "V_band", bn);
+            ba.diag_chol = diag_get(e, "V_chol", bn);
+            ba.diag_mean = diag_get(e, "V_mean", (size_t)e->P * e->K);
+            ba.diag_retries = e->diag_retries;
+            ba.resid_partials = gauss ? e->resid_partials + c.col_begin : nullptr;
+            launch_band_solve(ba, st); e->launches++;
+        }
+        phase_mark(e, PH_COMM);
+        if (e->shard) {
+            if (nccl_allgather_cols(e->shard, e->V, e->n, st)) return set_err(BTF_ENCCL, "all-gather(V) failed");
+        }
+        if (gauss && !c.resid_direct) {
+            // nu2 by-product: resid = ss_total + sum_j [v^T A v - 2 v.b]
+            if (e->shard) {
+                if (nccl_allgather_doubles(e->shard, e->resid_partials, st)) return set_err(BTF_ENCCL, "all-gather(resid) failed");
+            }
+            launch_set_resid(e->scal, e->resid_partials, e->M, st); e->launches++;
+            e->resid_valid = true;
+        }
+    } else {
+        phase_mark(e, PH_BAND_SOLVE);
+        phase_mark(e, PH_COMM);
+    }
+    phase_mark(e, PH_COUNT);
+    return BTF_OK;
+}
+
+static int check_info(btf_engine* e) {
+    CK(cudaMemcpyAsync(e->pinned_scal, e->scal, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    Scalars h;
+    memcpy(&h, e->pinned_scal, sizeof(h));
+    if (h.info_w > 0) return set_err(BTF_ENOTPD, "W step: Cholesky failed for %d row(s) (factor.py:357 has no retry)", h.info_w);
+    if (h.info_v > 0) return set_err(BTF_ENOTPD, "V step: Cholesky failed for %d column(s) after %d jitter attempts", h.info_v, e->cfg.force_psd_attempts);
+    return BTF_OK;
+}
+
+static bool graph_ok(btf_engine* e) {
+    return e->cfg.use_graph && !e->shard && e->inject.empty() && !e->diag && !e->time_phases &&
+           (e->resid_valid || e->cfg.likelihood != BTF_GAUSSIAN || e->cfg.resid_direct || !(e->cfg.sample_mask & BTF_SAMPLE_NU2));
+}
+
+static int build_graph(btf_engine* e) {
+    cudaGraph_t g = nullptr;
+    int64_t before = e->launches;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_sweep(e);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->graph_launches = (int)(e->launches - before);
+    e->launches = before;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) return set_err(BTF_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { e->graph_exec = nullptr; return set_err(BTF_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+    return BTF_OK;
+}
+
+// one sweep, by graph replay when the sequence is static
+static int one_sweep(btf_engine* e) {
+    if (graph_ok(e)) {
+        if (!e->graph_exec) { int rc = build_graph(e); if (rc) return rc; }
+        CK(cudaGraphLaunch(e->graph_exec, e->stream));
+        e->launches += e->graph_launches;
+        return BTF_OK;
+    }
+    int rc = enqueue_sweep(e);
+    if (!e->inject.empty()) {
+        // injected noise is consumed by exactly one sweep
+        CK(cudaStreamSynchronize(e->stream));
+        clear_inject(e);
+    }
+    return rc;
+}
+
+static int pre_run(btf_engine* e) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    if (!e->has_data) return set_err(BTF_ESTATE, "no data: call btf_set_data_* first");
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = ensure_data_reduced(e);
+    if (rc) return rc;
+    launch_clear_info(e->scal, e->stream); e->launches++;
+    return BTF_OK;
+}
+
+int btf_sweep(btf_engine* e, int32_t nsweeps) {
+    int rc = pre_run(e);
+    if (rc) return rc;
+    for (int s = 0; s < nsweeps; ++s) { rc = one_sweep(e); if (rc) return rc; }
+    return check_info(e);
+}
+
+int btf_sweep_timed(btf_engine* e, int32_t nsweeps, double* ms_out) {
+    int rc = pre_run(e);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(a, e->stream));
+    for (int s = 0; s < nsweeps; ++s) { rc = one_sweep(e); if (rc) break; }
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (ms_out) *ms_out = ms;
+    if (rc) return rc;
+    return check_info(e);
+}
+
+int btf_time_phases(btf_engine* e, int32_t nsweeps, double* ms_out, int32_t nphases) {
+    int rc = pre_run(e);
+    if (rc) return rc;
+    if (nphases < PH_COUNT) return set_err(BTF_EINVAL, "need room for %d phases", (int)PH_COUNT);
+    for (int i = 0; i < nphases; ++i) ms_out[i] = 0.0;
+    e->time_phases = true;
+    for (int s = 0; s < nsweeps; ++s) {
+        rc = enqueue_sweep(e);
+        if (rc) break;
+        CK(cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < PH_COUNT; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->ph_ev[i], e->ph_ev[i + 1]) == cudaSuccess) ms_out[i] += ms;
+            else cudaGetLastError();
+        }
+    }
+    e->time_phases = false;
+    for (int i = 0; i < PH_COUNT; ++i) ms_out[i] /= std::max(1, nsweeps);
+    if (rc) return rc;
+    return check_info(e);
+}
+
+int btf_synchronize(btf_engine* e) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    return BTF_OK;
+}
+
+__global__ void pack_scalars_kernel(const Scalars* s, double* out) {
+    out[0] = s->sigma2; out[1] = s->lam2; out[2] = s->nu2; out[3] = s->lam2_a;
+}
+
+// run_gibbs (genlasso.py:37-66), generalised to a segment of a chain: exactly `nsweeps`
+// sweeps; the state after local sweep indices first_save, first_save + nthin, ... is
+// written to sample slots sample_offset, sample_offset + 1, ...
+int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t nthin, int64_t sample_offset,
+                    double* W_out, double* V_out, double* Tau2_out, double* scalars_out, double* R_out,
+                    double* omega_out) {
+    int rc = pre_run(e);
+    if (rc) return rc;
+    if (nsweeps < 0 || nthin < 1 || first_save < 0 || sample_offset < 0) return set_err(BTF_EINVAL, "bad chain lengths");
+    const size_t wn = (size_t)e->N * e->K, vn = (size_t)e->P * e->K, tn = (size_t)e->M * e->RD;
+    const size_t rn = (size_t)e->Rn * e->Rm * e->Rt;
+    bool pending = false;
+    for (int step = 0; step < nsweeps; ++step) {
+        rc = one_sweep(e);
+        if (rc) return rc;
+        if (step >= first_save && (step - first_save) % nthin == 0) {
+            const size_t sidx = (size_t)sample_offset + (size_t)(step - first_save) / nthin;
+            // snapshot on the compute stream (device-to-device), drain on the copy stream
+            if (pending) CK(cudaStreamWaitEvent(e->stream, e->ev_copied, 0));
+            if (W_out) CK(cudaMemcpyAsync(e->snapW, e->W, wn * 8, cudaMemcpyDeviceToDevice, e->stream));
+            if (V_out) CK(cudaMemcpyAsync(e->snapV, e->V, vn * 8, cudaMemcpyDeviceToDevice, e->stream));
+            if (Tau2_out) CK(cudaMemcpyAsync(e->snapTau2, e->Tau2, tn * 8, cudaMemcpyDeviceToDevice, e->stream));
+            if (scalars_out) { pack_scalars_kernel<<<1, 1, 0, e->stream>>>(e->scal, e->snapScal); e->launches++; }
+            if (R_out && e->Rdisp) CK(cudaMemcpyAsync(e->snapR, e->Rdisp, rn * 8, cudaMemcpyDeviceToDevice, e->stream));
+            if (omega_out && e->omega) {
+                // omega is large: copy straight from the live buffer on the compute stream
+                CK(cudaMemcpy2DAsync(omega_out + sidx * (size_t)e->nloc * e->P, (size_t)e->P * 8, e->omega,
+                                     (size_t)e->Ppad * 8, (size_t)e->P * 8, e->nloc, cudaMemcpyDeviceToHost, e->stream));
+            }
+            CK(cudaEventRecord(e->ev_snap, e->stream));
+            CK(cudaStreamWaitEvent(e->copy_stream, e->ev_snap, 0));
+            if (W_out) CK(cudaMemcpyAsync(W_out + sidx * wn, e->snapW, wn * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+            if (V_out) CK(cudaMemcpyAsync(V_out + sidx * vn, e->snapV, vn * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+            if (Tau2_out) CK(cudaMemcpyAsync(Tau2_out + sidx * tn, e->snapTau2, tn * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+            if (scalars_out) CK(cudaMemcpyAsync(scalars_out + sidx * 4, e->snapScal, 4 * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+            if (R_out && e->Rdisp) CK(cudaMemcpyAsync(R_out + sidx * rn, e->snapR, rn * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+            CK(cudaEventRecord(e->ev_copied, e->copy_stream));
+            pending = true;
+        }
+    }
+    CK(cudaStreamSynchronize(e->copy_stream));
+    return check_info(e);
+}
+
+int btf_run(btf_engine* e, int32_t nburn, int32_t nthin, int32_t nsamples, double* W_out, double* V_out,
+            double* Tau2_out, double* scalars_out, double* R_out, double* omega_out) {
+    if (nburn < 0 || nthin < 1 || nsamples < 0) return set_err(BTF_EINVAL, "bad chain lengths");
+    return btf_run_segment(e, nburn + nthin * nsamples, nburn, nthin, 0, W_out, V_out, Tau2_out, scalars_out, R_out,
+                           omega_out);
+}
+
+// pinned host buffers for the result arrays (async device-to-host copies need them)
+void* btf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void btf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// Initial state drawn from the priors on the device (factor.py:230-253, 293-304, 560-563).
+// init_mask bits: 1 sigma2, 2 lam2(+lam2_a), 4 nu2, 8 Tau2(+a,b,c), 16 W, 32 V, 64 R
+int btf_init_state(btf_engine* e, int32_t init_mask) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    const btf_config& c = e->cfg;
+    cudaStream_t st = e->stream;
+    if (init_mask & 7) { launch_init_scalars(e->scal, c.seed, init_mask & 7, c.sigma2_a, c.sigma2_b, c.nu2_a, c.nu2_b, st); e->launches++; }
+    if (init_mask & 8) { launch_init_tau2(e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c, (size_t)e->M * e->RD, c.seed, st); e->launches++; }
+    if (init_mask & 16) { launch_init_W(e->W, e->N, e->K, e->scal, c.seed, st); e->launches++; }
+    if (init_mask & 32) {
+        // one prior MVN draw per column: the banded solver with zero statistics (factor.py:235-242)
+        BandSolveArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.stats = nullptr; ba.nsplit = 0; ba.split_stride = 0;
+        ba.col_begin = 0; ba.ncols_loc = e->M; ba.T = e->T; ba.K = e->K; ba.order = e->order; ba.RD = e->RD;
+        ba.homoskedastic = 0; ba.scal = e->scal; ba.Tau2 = e->Tau2;
+        ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
+        ba.V = e->V; ba.z_inject = nullptr; ba.seed = c.seed ^ 0x5bd1e995u;
+        double *wl = nullptr, *wy = nullptr;
+        const bool tmp = e->Mloc < e->M;   // sharded engines own a smaller workspace
+        if (tmp) {
+            CK(cudaMalloc((void**)&wl, (size_t)e->M * e->n * (e->kd + 1) * sizeof(double)));
+            CK(cudaMalloc((void**)&wy, (size_t)e->M * e->n * sizeof(double)));
+        }
+        ba.work_L = tmp ? wl : e->work_L; ba.work_y = tmp ? wy : e->work_y;
+        ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
+        launch_band_solve(ba, st);
+        launch_clip(e->V, (size_t)e->P * e->K, -10.0, 10.0, st);
+        e->launches += 2;
+        CK(cudaStreamSynchronize(st));
+        if (wl) cudaFree(wl);
+        if (wy) cudaFree(wy);
+    }
+    if ((init_mask & 64) && e->Rdisp) {
+        // R = exp(N(0, rstdev)) + 1  (factor.py:560-563), drawn on the host side of the ABI
+        const size_t rn = (size_t)e->Rn * e->Rm * e->Rt;
+        std::vector<double> r(rn);
+        uint64_t x = c.seed * 6364136223846793005ull + 1442695040888963407ull;
+        auto u01 = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return ((x >> 11) + 0.5) / 9007199254740992.0; };
+        for (size_t i = 0; i < rn; ++i) {
+            double z = std::sqrt(-2.0 * std::log(u01())) * std::cos(6.283185307179586 * u01());
+            r[i] = std::exp(c.rstdev * z) + 1.0;
+        }
+        CK(cudaMemcpy(e->Rdisp, r.data(), rn * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CK(cudaStreamSynchronize(st));
+    e->resid_valid = false;
+    return check_info(e);
+}
+
+// ------------------------------------------------------------------ sampler test hooks
+int btf_pg_sample(int32_t device, const double* b, const double* z, double* out, int64_t n, uint64_t seed) {
+    if (!b || !z || !out || n < 1) return set_err(BTF_EINVAL, "bad arguments");
+    CK(cudaSetDevice(device));
+    double *db = nullptr, *dz = nullptr, *dout = nullptr;
+    CK(cudaMalloc((void**)&db, n * 8)); CK(cudaMalloc((void**)&dz, n * 8)); CK(cudaMalloc((void**)&dout, n * 8));
+    CK(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dz, z, n * 8, cudaMemcpyHostToDevice));
+    launch_pg_sample(db, dz, dout, n, seed, 1ull, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(db); cudaFree(dz); cudaFree(dout);
+    return BTF_OK;
+}
+
+int btf_rng_sample(int32_t device, int32_t kind, double param, double* out, int64_t n, uint64_t seed) {
+    if (!out || n < 1) return set_err(BTF_EINVAL, "bad arguments");
+    CK(cudaSetDevice(device));
+    double* dout = nullptr;
+    CK(cudaMalloc((void**)&dout, n * 8));
+    launch_rng_sample(kind, param, dout, n, seed, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dout);
+    return BTF_OK;
+}
+
+// ------------------------------------------------------------------ NCCL plumbing
+int btf_nccl_unique_id(char* id128) {
+    if (!id128) return set_err(BTF_EINVAL, "null argument");
+    if (nccl_shard_unique_id(id128)) return set_err(BTF_ENCCL, "ncclGetUniqueId failed: %s", nccl_shard_error());
+    return BTF_OK;
+}
+
+int btf_nccl_init(btf_engine* e, const char* id128) {
+    if (!e || !id128) return set_err(BTF_EINVAL, "null argument");
+    if (e->cfg.world_size <= 1) return BTF_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    e->shard = nccl_shard_create(id128, e->cfg.world_size, e->cfg.rank, e->N, e->M, e->cfg.row_begin, e->cfg.row_end,
+                                 e->cfg.col_begin, e->cfg.col_end);
+    if (!e->shard) return set_err(BTF_ENCCL, "NCCL init failed: %s", nccl_shard_error());
+    return BTF_OK;
+}

@@ -1,0 +1,144 @@
+// Host-side launchers of the BTF kernels (one translation unit per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace btf {
+
+// ---------------------------------------------------------------- K0 prereduce
+// Y chunk [rows][P][R] (NaN = missing) -> cnt u8, S f64 at pitch `ld`; per-block
+// partial (sum of squares, #observed) appended to `partials` [2*nblocks].
+void launch_prereduce_gaussian(const double* Y, int rows, int P, int R, uint8_t* cnt, double* S,
+                               long long ld, double* partials, int* nblocks_out, cudaStream_t st);
+// Binomial: (Ysucc, Ntrials) [rows][P] -> obs u8, kappa = y - n/2, ntr = n (0 where missing)
+void launch_prereduce_binomial(const double* Y, const double* Nt, int rows, int P, uint8_t* obs,
+                               double* kappa, double* ntr, long long ld, cudaStream_t st);
+// dst[0] += sum(src[0..n) step stride) in a fixed order (single block)
+void launch_reduce_add(const double* src, int n, int stride, double* dst, cudaStream_t st);
+
+// ---------------------------------------------------------------- K1 statistics
+struct StatsPlan {
+    int cfg;          // 0: BM=128 (K<=16), 1: BM=32 (K<=32), 2: BM=128 small (K<=8)
+    int K, L, nct_z, nct_f, zw;
+    int BM, KC;
+    int mtiles, nchunks, nsplit, chunks_per_split;
+    size_t smem_bytes;
+    size_t out_elems_per_split;   // m_valid * (L+K)
+};
+// trans=false: row statistics (m = local row, contraction over p = (j,t));
+// trans=true : column statistics (m = p, contraction over local rows).
+// weights_f64: weight operand is double (omega) instead of uint8 counts.
+bool plan_stats(StatsPlan* plan, int K, bool trans, bool weights_f64, int mdim_pad, int kdim_pad,
+                int m_valid, int nsplit_request, int sm_count);
+void launch_stats(const StatsPlan& plan, bool trans, bool weights_f64, const void* wt, const double* sv,
+                  const double* F, long long ld, int m_valid, double* out, cudaStream_t st);
+
+// ---------------------------------------------------------------- residual (nu2)
+// resid_partials[b] = sum over the block's cells of cnt*Mu^2 - 2*Mu*S
+void launch_residual(const uint8_t* cnt, const double* S, long long ld, const double* W, const double* V,
+                     int nrows_pad, int Ppad, int K, double* partials, int* nblocks_out, cudaStream_t st);
+
+// ---------------------------------------------------------------- K2 row solve
+struct RowSolveArgs {
+    const double* stats;   // [nsplit][nloc][L+K]
+    int nsplit; size_t split_stride;
+    int nloc, row_begin, K;
+    const double* scale_from_nu2;   // Scalars* (uses 1/nu2) or nullptr (weights already scaled)
+    Scalars* scal;
+    double* W;             // global [N][K]
+    const double* z_inject;   // [N][K] or nullptr
+    uint64_t seed;
+    double *diag_Q, *diag_L, *diag_mean, *diag_b;   // optional [N][K][K], [N][K]
+};
+void launch_row_solve(const RowSolveArgs& a, int* nblocks_out, cudaStream_t st);
+
+// ---------------------------------------------------------------- K3 band solve
+struct BandSolveArgs {
+    const double* stats;   // [nsplit][P][L+K] (column statistics, unscaled)
+    int nsplit; size_t split_stride;
+    int col_begin, ncols_loc, T, K, order, RD;
+    int homoskedastic;     // 1: scale statistics by 1/nu2
+    Scalars* scal;
+    const double* Tau2;    // [M][RD]
+    const int* pm_ptr; const int* pm_row; const double* pm_coef;   // CSR of Delta^T diag Delta band
+    double* V;             // [M][T][K]
+    const double* z_inject;   // [M][T][K] or nullptr
+    uint64_t seed;
+    double* work_L;        // [ncols_loc][n][kd+1]
+    double* work_y;        // [ncols_loc][n]
+    int force_psd, attempts; double eps;
+    double *diag_band, *diag_chol, *diag_mean; int* diag_retries;
+    double* resid_partials;   // [ncols_loc]: sum_t v^T A v - 2 v.b   (nu2 by-product)
+};
+void launch_band_solve(const BandSolveArgs& a, cudaStream_t st);
+
+// ---------------------------------------------------------------- K5 hyper-parameters
+struct HyperArgs {
+    Scalars* scal;
+    const double* V; int M, T, K, RD;
+    const int* d_start; const int* d_width; const double* d_coef; int d_maxw;   // Delta stencils
+    double *Tau2, *Tau2_a, *Tau2_b, *Tau2_c;
+    double stability;
+    const double* g_inject;   // [M][4][RD] or nullptr
+    uint64_t seed;
+    double* lam_partials;     // [M]: 0.5 * sum_{r,k} delta^2 / tau2   (new tau2)
+    int col_begin, col_end;
+};
+void launch_tau2(const HyperArgs& a, cudaStream_t st);
+struct ScalarStepArgs {
+    Scalars* scal; uint64_t seed;
+    double prior_a, prior_b;
+    const double* g_inject;   // standard gamma(s) or nullptr
+};
+// nu2 | rest : uses scal->resid, scal->n_obs
+void launch_nu2(const ScalarStepArgs& a, cudaStream_t st);
+// sigma2 | rest : uses scal->w_sumsq and n_free
+void launch_sigma2(const ScalarStepArgs& a, double n_free, cudaStream_t st);
+// lam2, lam2_a | rest
+void launch_lam2(const ScalarStepArgs& a, const double* lam_partials, int M, int ref_compat, double shape,
+                 cudaStream_t st);
+void launch_w_sumsq(const double* W, int N, int K, Scalars* scal, cudaStream_t st);
+void launch_bump_sweep(Scalars* scal, cudaStream_t st);
+void launch_clear_info(Scalars* scal, cudaStream_t st);
+void launch_set_resid(Scalars* scal, const double* partials, int n, cudaStream_t st);   // resid = ss_total + sum
+
+void launch_init_scalars(Scalars* s, uint64_t seed, int mask, double sigma2_a, double sigma2_b, double nu2_a,
+                         double nu2_b, cudaStream_t st);
+void launch_init_tau2(double* Tau2, double* Ta, double* Tb, double* Tc, size_t n, uint64_t seed, cudaStream_t st);
+void launch_init_W(double* W, int N, int K, const Scalars* s, uint64_t seed, cudaStream_t st);
+void launch_clip(double* x, size_t n, double lo, double hi, cudaStream_t st);
+
+// ---------------------------------------------------------------- K4 Polya-Gamma / negative binomial
+struct PgArgs {
+    const uint8_t* obs; const double* ntr; double* omega; long long ld;
+    const double* W; const double* V;     // W local rows [nloc_pad][K], V [Ppad][K]
+    int nloc, nrows_pad, P, Ppad, K, row_begin;
+    Scalars* scal; uint64_t seed;
+};
+// omega[i,p] ~ PG(ntr[i,p], w_i . v_p) for observed cells, 0 elsewhere (factor.py:447-460)
+void launch_pg_draw(const PgArgs& a, cudaStream_t st);
+// standalone sampler for moment tests: out[e] ~ PG(b[e], z[e])
+void launch_pg_sample(const double* b, const double* z, double* out, long long n, uint64_t seed,
+                      unsigned long long sweep, cudaStream_t st);
+
+void launch_rng_sample(int kind, double param, double* out, long long n, uint64_t seed, cudaStream_t st);
+
+struct NbArgs {
+    const double* Yraw;      // [nloc][P][R] raw counts (NaN = missing), contiguous
+    int nloc, P, R, M, T, K, row_begin, nrows_global;
+    long long ld;
+    const double* W; const double* V;
+    double* Rdisp;           // dispersion, broadcast shape [Rn, Rm, Rt] (1 where shared)
+    int Rn, Rm, Rt;          // extents of R (1 or the dim)
+    int nmh; double rpropstdev, rstdev;
+    const double* z_inject; const double* u_inject;   // [nmh][Rsize] or nullptr
+    Scalars* scal; uint64_t seed;
+    double* work;            // scratch [>= 4 * Rsize + nblocks * Rsize ...]
+    uint8_t* obs; double* kappa; double* ntr;         // outputs of the pseudo-count refresh
+};
+// R | rest by nmh random-walk MH steps on log R, then N = sum_r (y + R), kappa = sum_r y - N/2
+// (factor.py:513-554, 494-511)
+void launch_nb_update(const NbArgs& a, cudaStream_t st);
+
+}  // namespace btf

@@ -1,0 +1,176 @@
+#include "nccl_shard.h"
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+namespace btf {
+
+// minimal NCCL ABI (nccl.h): opaque comm, 128-byte unique id, enums
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt32 = 2, ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_api;
+static char g_nccl_err[256] = "";
+const char* nccl_shard_error() { return g_nccl_err; }
+
+static bool load_api() {
+    if (g_api.h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_api.h) break;
+    }
+    if (!g_api.h) { snprintf(g_nccl_err, sizeof(g_nccl_err), "cannot dlopen libnccl.so.2: %s", dlerror()); return false; }
+#define SYM(field, name) *(void**)(&g_api.field) = dlsym(g_api.h, name); if (!g_api.field) { snprintf(g_nccl_err, sizeof(g_nccl_err), "missing symbol %s", name); return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(Reduce, "ncclReduce")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+}
+
+#define NC(call)                                                                               \
+    do {                                                                                       \
+        int _r = (call);                                                                       \
+        if (_r != ncclSuccess) {                                                               \
+            snprintf(g_nccl_err, sizeof(g_nccl_err), "%s: %s", #call, g_api.GetErrorString(_r)); \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+struct NcclShard {
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0, N = 0, M = 0;
+    std::vector<int> rb, re, cb, ce;   // per-rank [begin, end) of rows and columns
+    double* scratch = nullptr;
+};
+
+int nccl_shard_unique_id(char* id128) {
+    if (!load_api()) return -1;
+    ncclUniqueId id;
+    NC(g_api.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+NcclShard* nccl_shard_create(const char* id128, int world, int rank, int N, int M, int row_begin, int row_end,
+                             int col_begin, int col_end) {
+    if (!load_api()) return nullptr;
+    NcclShard* s = new NcclShard();
+    s->world = world; s->rank = rank; s->N = N; s->M = M;
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    int r = g_api.CommInitRank(&s->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        snprintf(g_nccl_err, sizeof(g_nccl_err), "ncclCommInitRank: %s", g_api.GetErrorString(r));
+        delete s; return nullptr;
+    }
+    // exchange the shard boundaries
+    int* dev = nullptr;
+    cudaMalloc((void**)&dev, sizeof(int) * 4 * (world + 1));
+    int mine[4] = {row_begin, row_end, col_begin, col_end};
+    cudaMemcpy(dev + 4 * world, mine, sizeof(mine), cudaMemcpyHostToDevice);
+    r = g_api.AllGather(dev + 4 * world, dev, 4, ncclInt32, s->comm, 0);
+    cudaError_t ce = cudaDeviceSynchronize();
+    std::vector<int> all(4 * world);
+    cudaMemcpy(all.data(), dev, sizeof(int) * 4 * world, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (r != ncclSuccess || ce != cudaSuccess) {
+        snprintf(g_nccl_err, sizeof(g_nccl_err), "boundary all-gather failed");
+        g_api.CommDestroy(s->comm); delete s; return nullptr;
+    }
+    for (int k = 0; k < world; ++k) {
+        s->rb.push_back(all[4 * k]); s->re.push_back(all[4 * k + 1]);
+        s->cb.push_back(all[4 * k + 2]); s->ce.push_back(all[4 * k + 3]);
+    }
+    cudaMalloc((void**)&s->scratch, 8 * sizeof(double));
+    return s;
+}
+
+void nccl_shard_destroy(NcclShard* s) {
+    if (!s) return;
+    if (s->comm) g_api.CommDestroy(s->comm);
+    if (s->scratch) cudaFree(s->scratch);
+    delete s;
+}
+
+static int gather_blocks(NcclShard* s, double* base, const std::vector<int>& b, const std::vector<int>& e, size_t unit,
+                         cudaStream_t st) {
+    NC(g_api.GroupStart());
+    for (int r = 0; r < s->world; ++r) {
+        size_t cnt = (size_t)(e[r] - b[r]) * unit;
+        if (cnt == 0) continue;
+        double* p = base + (size_t)b[r] * unit;
+        NC(g_api.Broadcast(p, p, cnt, ncclFloat64, r, s->comm, st));
+    }
+    NC(g_api.GroupEnd());
+    return 0;
+}
+
+int nccl_allgather_rows(NcclShard* s, double* W, int K, cudaStream_t st) { return gather_blocks(s, W, s->rb, s->re, K, st); }
+int nccl_allgather_cols(NcclShard* s, double* V, int n, cudaStream_t st) { return gather_blocks(s, V, s->cb, s->ce, n, st); }
+int nccl_allgather_doubles(NcclShard* s, double* v, cudaStream_t st) { return gather_blocks(s, v, s->cb, s->ce, 1, st); }
+
+__global__ void collapse_splits_kernel(double* x, int nsplit, size_t stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < stride; i += (size_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        for (int s = 1; s < nsplit; ++s) v += x[(size_t)s * stride + i];
+        x[i] = v;
+    }
+}
+
+int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,
+                          cudaStream_t st) {
+    if (nsplit > 1) collapse_splits_kernel<<<148 * 8, 256, 0, st>>>(col_stats, nsplit, split_stride);
+    NC(g_api.GroupStart());
+    for (int r = 0; r < s->world; ++r) {
+        size_t cnt = (size_t)(s->ce[r] - s->cb[r]) * per_col_elems;
+        if (cnt == 0) continue;
+        double* p = col_stats + (size_t)s->cb[r] * per_col_elems;
+        NC(g_api.Reduce(p, p, cnt, ncclFloat64, ncclSum, r, s->comm, st));
+    }
+    NC(g_api.GroupEnd());
+    return 0;
+}
+
+int nccl_allreduce_sum(NcclShard* s, double* p, int n, cudaStream_t st) {
+    NC(g_api.AllReduce(p, p, (size_t)n, ncclFloat64, ncclSum, s->comm, st));
+    return 0;
+}
+
+__global__ void resid_local_kernel(const Scalars* sc, double* tmp) { tmp[0] = sc->resid - sc->ss_total; }
+__global__ void resid_global_kernel(Scalars* sc, const double* tmp) { sc->resid = sc->ss_total + tmp[0]; }
+
+int nccl_allreduce_resid(NcclShard* s, Scalars* scal, cudaStream_t st) {
+    resid_local_kernel<<<1, 1, 0, st>>>(scal, s->scratch);
+    NC(g_api.AllReduce(s->scratch, s->scratch, 1, ncclFloat64, ncclSum, s->comm, st));
+    resid_global_kernel<<<1, 1, 0, st>>>(scal, s->scratch);
+    return 0;
+}
+
+}  // namespace btf

@@ -1,0 +1,31 @@
+// Exchange steps of the row/column-sharded sweep over NCCL.
+// NCCL is loaded lazily with dlopen so the single-GPU path has no NCCL dependency.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace btf {
+
+struct NcclShard;
+
+int nccl_shard_unique_id(char* id128);
+const char* nccl_shard_error();
+NcclShard* nccl_shard_create(const char* id128, int world, int rank, int N, int M, int row_begin, int row_end,
+                             int col_begin, int col_end);
+void nccl_shard_destroy(NcclShard* s);
+
+// in-place all-gather of the row blocks of W [N][K]
+int nccl_allgather_rows(NcclShard* s, double* W, int K, cudaStream_t st);
+// in-place all-gather of the column blocks of V [M][n]
+int nccl_allgather_cols(NcclShard* s, double* V, int n, cudaStream_t st);
+// in-place all-gather of a per-column vector [M]
+int nccl_allgather_doubles(NcclShard* s, double* v, cudaStream_t st);
+// collapse the split partials into split 0, then sum across ranks so that every rank
+// holds the totals of ITS column block (a reduce-scatter with uneven blocks)
+int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,
+                          cudaStream_t st);
+int nccl_allreduce_sum(NcclShard* s, double* p, int n, cudaStream_t st);
+// scal->resid currently holds ss_total + (local partial); make it ss_total + sum of all partials
+int nccl_allreduce_resid(NcclShard* s, Scalars* scal, cudaStream_t st);
+
+}  // namespace btf

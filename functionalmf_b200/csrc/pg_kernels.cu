@@ -1,0 +1,319 @@
+// K4a: on-device Polya-Gamma sampler (replaces pypolyagamma's pgdrawv, factor.py:431-432, 459)
+// K4c: negative-binomial dispersion update by random-walk MH (factor.py:513-554)
+//
+// PG(1, z): Devroye's exact alternating-series sampler (Polson, Scott & Windle 2013,
+// Alg. 1; truncation t = 0.64).  PG(b, z): floor(b) such draws + truncated
+// sum-of-gammas for the fractional part (expected tail added back); b > 170: the
+// moment-matched normal approximation (the rule of the hybrid sampler the
+// reference's third-party dependency implements).  All randomness is Philox,
+// keyed by (seed, sweep, global cell index).
+#include "kernels.h"
+
+namespace btf {
+
+#define PG_TRUNC 0.64
+#define PG_PI 3.14159265358979323846
+#define PG_NORMAL_B 170.0
+#define PG_SERIES 200
+
+__device__ __forceinline__ double log_phi(double x) {
+    if (x > -5.0) return log(0.5 * erfc(-x * 0.70710678118654752440));
+    double u = -x * 0.70710678118654752440;
+    return log(0.5 * erfcx(u)) - u * u;
+}
+
+struct PgTilt { double Z, fz, pmass; };
+
+__device__ __forceinline__ PgTilt pg_setup(double z) {
+    PgTilt c;
+    c.Z = 0.5 * fabs(z);
+    c.fz = PG_PI * PG_PI / 8.0 + 0.5 * c.Z * c.Z;
+    const double rt = 1.25;   // sqrt(1 / 0.64)
+    double b = rt * (PG_TRUNC * c.Z - 1.0), a = -rt * (PG_TRUNC * c.Z + 1.0);
+    double x0 = log(c.fz) + c.fz * PG_TRUNC;
+    double qdivp = 4.0 / PG_PI * (exp(x0 - c.Z + log_phi(b)) + exp(x0 + c.Z + log_phi(a)));
+    c.pmass = 1.0 / (1.0 + qdivp);
+    return c;
+}
+
+__device__ __forceinline__ double pg_acoef(int n, double x) {
+    const double k = (n + 0.5) * PG_PI;
+    if (x > PG_TRUNC) return k * exp(-0.5 * k * k * x);
+    return exp(-1.5 * (log(0.5 * PG_PI) + log(x)) + log(k) - 2.0 * (n + 0.5) * (n + 0.5) / x);
+}
+
+__device__ double pg_rtigauss(Rng& rng, double Z) {
+    const double t = PG_TRUNC;
+    if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0)
+        for (int it = 0; it < 10000; ++it) {
+            double e1, e2;
+            for (int k = 0; k < 10000; ++k) {
+                double2 u = rng.uniform2();
+                e1 = -log(u.x); e2 = -log(u.y);
+                if (e1 * e1 <= 2.0 * e2 / t) break;
+            }
+            double X = t / ((1.0 + t * e1) * (1.0 + t * e1));
+            if (rng.uniform() <= exp(-0.5 * Z * Z * X)) return X;
+        }
+        return t;
+    }
+    const double mu = 1.0 / Z;
+    for (int it = 0; it < 10000; ++it) {
+        double nn = rng.normal();
+        double Y = nn * nn;
+        double X = mu + 0.5 * mu * mu * Y - 0.5 * mu * sqrt(4.0 * mu * Y + (mu * Y) * (mu * Y));
+        if (rng.uniform() > mu / (mu + X)) X = mu * mu / X;
+        if (X <= t) return X;
+    }
+    return t;
+}
+
+__device__ double pg_one(Rng& rng, const PgTilt& c) {
+    for (int it = 0; it < 10000; ++it) {
+        double X;
+        if (rng.uniform() < c.pmass) X = PG_TRUNC + rng.exponential() / c.fz;
+        else X = pg_rtigauss(rng, c.Z);
+        double S = pg_acoef(0, X);
+        const double Y = rng.uniform() * S;
+        for (int n = 1; n < 400; ++n) {
+            if (n & 1) { S -= pg_acoef(n, X); if (Y <= S) return 0.25 * X; }
+            else { S += pg_acoef(n, X); if (Y > S) break; }
+        }
+    }
+    return 0.25 * PG_TRUNC;
+}
+
+__device__ __forceinline__ double pg_mean(double b, double z) {
+    z = fabs(z);
+    if (z < 1e-6) return b * 0.25 * (1.0 - z * z / 12.0);
+    return b * tanh(0.5 * z) / (2.0 * z);
+}
+__device__ __forceinline__ double pg_var(double b, double z) {
+    z = fabs(z);
+    if (z < 1e-3) return b * (1.0 / 24.0) * (1.0 - z * z * 0.2);
+    double ch = cosh(0.5 * z);
+    return b * (sinh(z) - z) / (4.0 * z * z * z * ch * ch);
+}
+
+__device__ double pg_draw(Rng& rng, double b, double z) {
+    if (!(b > 0.0) || isinf(b) || !(z == z) || isinf(z)) return 0.0;
+    if (b > PG_NORMAL_B) {
+        double v = pg_mean(b, z) + sqrt(pg_var(b, z)) * rng.normal();
+        return v > 0.0 ? v : pg_mean(b, z);
+    }
+    const PgTilt c = pg_setup(z);
+    const int bi = (int)floor(b);
+    const double bf = b - bi;
+    double acc = 0.0;
+    for (int k = 0; k < bi; ++k) acc += pg_one(rng, c);
+    if (bf > 1e-12) {
+        double s = 0.0, dsum = 0.0;
+        for (int k = 1; k <= PG_SERIES; ++k) {
+            double km = k - 0.5;
+            double d = 4.0 * PG_PI * PG_PI * km * km + z * z;
+            s += rng.gamma(bf) / d;
+            dsum += 1.0 / d;
+        }
+        acc += 2.0 * s + (pg_mean(bf, z) - 2.0 * bf * dsum);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------- omega ~ PG(ntr, w.v)
+template <int KMAX>
+__global__ void __launch_bounds__(256) pg_draw_kernel(PgArgs a) {
+    __shared__ double ws[32 * KMAX];
+    const int K = a.K;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const int i0 = blockIdx.y * 32;
+    for (int e = threadIdx.x; e < 32 * K; e += 256) ws[e] = a.W[(size_t)i0 * K + e];
+    double v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) v[k] = (k < K && p < a.Ppad) ? a.V[(size_t)p * K + k] : 0.0;
+    __syncthreads();
+    if (p >= a.P) return;
+    const unsigned long long sweep = a.scal->sweep;
+    for (int r = 0; r < 32; ++r) {
+        const int il = i0 + r;
+        if (il >= a.nloc) break;
+        const size_t o = (size_t)il * a.ld + p;
+        double om = 0.0;
+        if (a.obs[o]) {
+            double psi = 0.0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) psi += ws[r * K + k] * v[k];
+            Rng rng(a.seed, STREAM_PG, sweep, (uint64_t)(a.row_begin + il) * a.P + p);
+            om = pg_draw(rng, a.ntr[o], psi);
+        }
+        a.omega[o] = om;
+    }
+}
+
+void launch_pg_draw(const PgArgs& a, cudaStream_t st) {
+    dim3 grid((a.P + 255) / 256, (a.nloc + 31) / 32);
+    if (a.K <= 8) pg_draw_kernel<8><<<grid, 256, 0, st>>>(a);
+    else if (a.K <= 16) pg_draw_kernel<16><<<grid, 256, 0, st>>>(a);
+    else pg_draw_kernel<32><<<grid, 256, 0, st>>>(a);
+}
+
+__global__ void pg_sample_kernel(const double* b, const double* z, double* out, long long n, uint64_t seed,
+                                 unsigned long long sweep) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    Rng rng(seed, STREAM_PG, sweep, (uint64_t)e);
+    out[e] = pg_draw(rng, b[e], z[e]);
+}
+void launch_pg_sample(const double* b, const double* z, double* out, long long n, uint64_t seed,
+                      unsigned long long sweep, cudaStream_t st) {
+    pg_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b, z, out, n, seed, sweep);
+}
+
+// raw variates of the device generator, for moment tests: kind 0 normal, 1 gamma(param),
+// 2 exponential, 3 uniform
+__global__ void rng_sample_kernel(int kind, double param, double* out, long long n, uint64_t seed) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    Rng rng(seed, 99u, 1ull, (uint64_t)e);
+    double v;
+    if (kind == 0) v = rng.normal();
+    else if (kind == 1) v = rng.gamma(param);
+    else if (kind == 2) v = rng.exponential();
+    else v = rng.uniform();
+    out[e] = v;
+}
+void launch_rng_sample(int kind, double param, double* out, long long n, uint64_t seed, cudaStream_t st) {
+    rng_sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kind, param, out, n, seed);
+}
+
+// ---------------------------------------------------------------- negative-binomial R
+// work layout (Rs = number of R entries):
+//   logR[Rs] cand[Rs] candlog[Rs] lg_cur[Rs] lg_cand[Rs] slog[Rs] ng[Rs]
+__device__ __forceinline__ int nb_group(const NbArgs& a, int i, int j, int t) {
+    return ((a.Rn > 1 ? i : 0) * a.Rm + (a.Rm > 1 ? j : 0)) * a.Rt + (a.Rt > 1 ? t : 0);
+}
+
+// per cell: psi -> log(1-P); accumulate slog_g, n_g and lg_cur_g = sum lgamma(y + R_g)
+__global__ void nb_prepare_kernel(NbArgs a) {
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    double *logR = a.work, *lg_cur = a.work + 3 * Rs, *slog = a.work + 5 * Rs, *ng = a.work + 6 * Rs;
+    const long long cells = (long long)a.nloc * a.P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
+        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+        const int j = p / a.T, t = p - j * a.T;
+        const int g = nb_group(a, a.row_begin + il, j, t);
+        const double* y = a.Yraw + e * a.R;
+        int c = 0;
+        double lg = 0.0;
+        const double Rg = a.Rdisp[g];
+        for (int r = 0; r < a.R; ++r) {
+            double v = y[r];
+            if (v == v) { ++c; lg += lgamma(v + Rg); }
+        }
+        if (c) {
+            double psi = 0.0;
+            for (int k = 0; k < a.K; ++k) psi += a.W[(size_t)il * a.K + k] * a.V[(size_t)p * a.K + k];
+            psi = clampd(psi, -10.0, 10.0);
+            const double Pr = 1.0 / (1.0 + exp(-psi));      // ilogit as in utils.py:106-107
+            atomicAdd(&slog[g], c * log(1.0 - Pr));
+            atomicAdd(&ng[g], (double)c);
+            atomicAdd(&lg_cur[g], lg);
+        }
+    }
+    (void)logR;
+}
+
+__global__ void nb_init_kernel(NbArgs a) {
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= Rs) return;
+    a.work[g] = log(a.Rdisp[g]);
+    a.work[3 * Rs + g] = 0.0; a.work[4 * Rs + g] = 0.0; a.work[5 * Rs + g] = 0.0; a.work[6 * Rs + g] = 0.0;
+}
+
+// accept/reject the pending proposal of step `step-1` (if any), then propose for `step`
+__global__ void nb_mh_kernel(NbArgs a, int step) {
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= Rs) return;
+    double *logR = a.work, *cand = a.work + Rs, *candlog = a.work + 2 * Rs, *lg_cur = a.work + 3 * Rs,
+           *lg_cand = a.work + 4 * Rs, *slog = a.work + 5 * Rs, *ng = a.work + 6 * Rs;
+    const unsigned long long sweep = a.scal->sweep;
+    if (step > 0) {
+        const int s = step - 1;
+        const double R = a.Rdisp[g], Rc = cand[g], l = logR[g], lc = candlog[g];
+        const double dprior = -(lc * lc - l * l) / (2.0 * a.rstdev * a.rstdev);
+        const double ll = lg_cand[g] - lg_cur[g] - ng[g] * (lgamma(Rc) - lgamma(R)) + (Rc - R) * slog[g];
+        const double prob = exp(clampd(dprior + ll, -10.0, 1.0));
+        double u;
+        if (a.u_inject) u = a.u_inject[(size_t)s * Rs + g];
+        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s + 1) * Rs + g); u = rng.uniform(); }
+        if (u <= prob && Rc > 1.0) { a.Rdisp[g] = Rc; logR[g] = lc; lg_cur[g] = lg_cand[g]; }
+    }
+    if (step < a.nmh) {
+        double z;
+        if (a.z_inject) z = a.z_inject[(size_t)step * Rs + g];
+        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * step) * Rs + g); z = rng.normal(); }
+        const double lc = logR[g] + a.rpropstdev * z;
+        candlog[g] = lc;
+        cand[g] = exp(lc);
+        lg_cand[g] = 0.0;
+    }
+}
+
+__global__ void nb_lgamma_kernel(NbArgs a) {
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    const double* cand = a.work + Rs;
+    double* lg_cand = a.work + 4 * Rs;
+    const long long cells = (long long)a.nloc * a.P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
+        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+        const int j = p / a.T, t = p - j * a.T;
+        const int g = nb_group(a, a.row_begin + il, j, t);
+        const double* y = a.Yraw + e * a.R;
+        const double Rc = cand[g];
+        double lg = 0.0;
+        bool any = false;
+        for (int r = 0; r < a.R; ++r) { double v = y[r]; if (v == v) { lg += lgamma(v + Rc); any = true; } }
+        if (any) atomicAdd(&lg_cand[g], lg);
+    }
+}
+
+// pseudo-counts of the PG step: N = sum_obs (y + R), kappa = sum_obs y - N/2 (factor.py:553, 507-508, 439)
+__global__ void nb_counts_kernel(NbArgs a) {
+    const long long cells = (long long)a.nloc * a.P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
+        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+        const int j = p / a.T, t = p - j * a.T;
+        const double Rg = a.Rdisp[nb_group(a, a.row_begin + il, j, t)];
+        const double* y = a.Yraw + e * a.R;
+        double ys = 0.0, ns = 0.0;
+        int c = 0;
+        for (int r = 0; r < a.R; ++r) { double v = y[r]; if (v == v) { ys += v; ns += v + Rg; ++c; } }
+        const size_t o = (size_t)il * a.ld + p;
+        a.obs[o] = c ? 1 : 0;
+        a.ntr[o] = c ? ns : 0.0;
+        a.kappa[o] = c ? ys - 0.5 * ns : 0.0;
+    }
+}
+
+void launch_nb_update(const NbArgs& a, cudaStream_t st) {
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    const long long cells = (long long)a.nloc * a.P;
+    int nb = (int)((cells + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    const int gb = (Rs + 127) / 128;
+    if (a.nmh > 0) {
+        nb_init_kernel<<<gb, 128, 0, st>>>(a);
+        nb_prepare_kernel<<<nb, 256, 0, st>>>(a);
+        for (int s = 0; s < a.nmh; ++s) {
+            nb_mh_kernel<<<gb, 128, 0, st>>>(a, s);
+            nb_lgamma_kernel<<<nb, 256, 0, st>>>(a);
+        }
+        nb_mh_kernel<<<gb, 128, 0, st>>>(a, a.nmh);
+    }
+    nb_counts_kernel<<<nb, 256, 0, st>>>(a);
+}
+
+}  // namespace btf

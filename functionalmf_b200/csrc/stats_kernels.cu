@@ -1,0 +1,451 @@
+// K0 (replicate pre-reduction), K1 (NaN-masked sufficient-statistic contractions
+// on the FP64 tensor pipe) and the nu2 residual pass.
+//
+// K1 replaces the per-row / per-column Python loops of the reference
+// (factor.py:333-360 for W, factor.py:378-401 for V; the latter builds
+// kron(W, I_T)[~missing] and two sparse products per column).  Both are the same
+// GEMM-shaped contraction
+//     out[m, c] = sum_k  A[m, k] * Z[k, c]
+// with a *generated* right operand: Z[k, (k1,k2)] = F[k,k1] F[k,k2] for the packed
+// lower triangle (L = K(K+1)/2 columns, weight operand A = counts or omega) and
+// Z[k, L + k1] = F[k,k1] (K columns, A = replicate sums / kappa).
+//   row statistics  (trans = false): m = row i, k = p = (j,t), F = V
+//   col statistics  (trans = true ): m = p = (j,t), k = row i, F = W
+// The data operand is read once from HBM with coalesced 16-byte cp.async into a
+// two-stage shared-memory ring; Z tiles are generated on chip from the small
+// factor tile; products run as mma.sync.m8n8k4.f64 (DMMA) -- tcgen05 has no FP64
+// kind, so this is the B200 FP64 tensor path.
+#include "kernels.h"
+#include <stdio.h>
+
+namespace btf {
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------ K0
+__global__ void prereduce_gaussian_kernel(const double* __restrict__ Y, int rows, int P, int R,
+                                          uint8_t* __restrict__ cnt, double* __restrict__ S, long long ld,
+                                          double* __restrict__ partials) {
+    __shared__ double sh[64];
+    double ss = 0.0, no = 0.0;
+    long long total = (long long)rows * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e / P), p = (int)(e - (long long)i * P);
+        const double* y = Y + e * R;
+        double s = 0.0;
+        int c = 0;
+        for (int r = 0; r < R; ++r) {
+            double v = y[r];
+            if (v == v) { s += v; ss += v * v; ++c; }
+        }
+        cnt[(long long)i * ld + p] = (uint8_t)c;
+        S[(long long)i * ld + p] = s;
+        no += (double)c;
+    }
+    double a = block_sum(ss, sh);
+    double b = block_sum(no, sh + 32);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = a; partials[2 * blockIdx.x + 1] = b; }
+}
+
+void launch_prereduce_gaussian(const double* Y, int rows, int P, int R, uint8_t* cnt, double* S,
+                               long long ld, double* partials, int* nblocks_out, cudaStream_t st) {
+    long long total = (long long)rows * P;
+    int nb = (int)((total + 255) / 256);
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb < 1) nb = 1;
+    prereduce_gaussian_kernel<<<nb, 256, 0, st>>>(Y, rows, P, R, cnt, S, ld, partials);
+    *nblocks_out = nb;
+}
+
+__global__ void prereduce_binomial_kernel(const double* __restrict__ Y, const double* __restrict__ Nt,
+                                          int rows, int P, uint8_t* __restrict__ obs,
+                                          double* __restrict__ kappa, double* __restrict__ ntr, long long ld) {
+    long long total = (long long)rows * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e / P), p = (int)(e - (long long)i * P);
+        double y = Y[e], n = Nt[e];
+        bool ok = (y == y) && (n == n);
+        long long o = (long long)i * ld + p;
+        obs[o] = ok ? 1 : 0;
+        kappa[o] = ok ? (y - 0.5 * n) : 0.0;
+        ntr[o] = ok ? n : 0.0;
+    }
+}
+
+void launch_prereduce_binomial(const double* Y, const double* Nt, int rows, int P, uint8_t* obs,
+                               double* kappa, double* ntr, long long ld, cudaStream_t st) {
+    long long total = (long long)rows * P;
+    int nb = (int)((total + 255) / 256);
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb < 1) nb = 1;
+    prereduce_binomial_kernel<<<nb, 256, 0, st>>>(Y, Nt, rows, P, obs, kappa, ntr, ld);
+}
+
+__global__ void reduce_add_kernel(const double* __restrict__ src, int n, int stride, double* dst) {
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += src[(long long)i * stride];
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) dst[0] += v;
+}
+void launch_reduce_add(const double* src, int n, int stride, double* dst, cudaStream_t st) {
+    reduce_add_kernel<<<1, 256, 0, st>>>(src, n, stride, dst);
+}
+
+// ------------------------------------------------------------------ K1
+struct StatsKArgs {
+    const void* wt;
+    const double* sv;
+    const double* F;
+    double* out;
+    long long ld;
+    int K, L, nct_z, nct_f, zw;
+    int nchunks, chunks_per_split;
+    int m_valid;
+    long long out_split_stride;
+};
+
+template <bool TRANS, typename WT, int BM, int KC>
+struct TileGeom {
+    // shared-memory row strides (elements) chosen so that the DMMA fragment reads
+    // are bank-conflict free and every cp.async destination is 16-byte aligned
+    static constexpr int WROWS = TRANS ? KC : BM;
+    static constexpr int WSTR = sizeof(WT) == 1 ? (TRANS ? BM + 16 : 48) : (TRANS ? BM + 8 : KC + 4);
+    static constexpr int SSTR = TRANS ? BM + 8 : KC + 4;
+    static constexpr int WBYTES = WROWS * WSTR * (int)sizeof(WT);
+    static constexpr int SBYTES = WROWS * SSTR * 8;
+};
+
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+__global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
+    constexpr int NT = 32 * WR * WC;
+    constexpr int RT = BM / 8 / WR;
+    constexpr int CZ = (CTM * WC * 8 + 31) / 32;
+    using G = TileGeom<TRANS, WT, BM, KC>;
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const int K = a.K, L = a.L, nct_z = a.nct_z, nct = a.nct_z + a.nct_f, zw = a.zw;
+    const int ncw = nct * 8;
+    const int fbytes = ((KC * K * 8) + 15) & ~15;
+    const int stage_bytes = G::WBYTES + G::SBYTES + fbytes;
+    unsigned char* stage0 = smem;
+    double* ztile = reinterpret_cast<double*>(smem + 2 * stage_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp / WC, wc = warp % WC;
+    const int m0 = blockIdx.x * BM;
+    const int split = blockIdx.y;
+    const int c_begin = split * a.chunks_per_split;
+    const int c_end = min(a.nchunks, c_begin + a.chunks_per_split);
+
+    // which generated column(s) this lane fills during Z generation
+    // code: bit31..30 type (0 zero, 1 product, 2 copy), k1 = bits 8..15, k2 = bits 0..7
+    int zcode[CZ];
+#pragma unroll
+    for (int q = 0; q < CZ; ++q) {
+        int c = lane + 32 * q;
+        int code = 0;
+        if (c < ncw) {
+            if (c < nct_z * 8) {
+                if (c < L) {
+                    int k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
+                    while (k1 * (k1 + 1) / 2 > c) --k1;
+                    while ((k1 + 1) * (k1 + 2) / 2 <= c) ++k1;
+                    int k2 = c - k1 * (k1 + 1) / 2;
+                    code = (1 << 30) | (k1 << 8) | k2;
+                }
+            } else {
+                int cf = c - nct_z * 8;
+                if (cf < K) code = (2 << 30) | (cf << 8);
+            }
+        }
+        zcode[q] = code;
+    }
+
+    double acc[RT][CTM][2];
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int c = 0; c < CTM; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    auto load_chunk = [&](int stage, int chunk) {
+        unsigned char* base = stage0 + stage * stage_bytes;
+        WT* wtile = reinterpret_cast<WT*>(base);
+        double* stile = reinterpret_cast<double*>(base + G::WBYTES);
+        double* ftile = reinterpret_cast<double*>(base + G::WBYTES + G::SBYTES);
+        const int k0 = chunk * KC;
+        const WT* wsrc = reinterpret_cast<const WT*>(a.wt);
+        if (!TRANS) {
+            // rows m0..m0+BM of the data, columns k0..k0+KC
+            constexpr int WP = KC * (int)sizeof(WT) / 16;   // 16-byte pieces per row
+            for (int e = tid; e < BM * WP; e += NT) {
+                int r = e / WP, q = e % WP;
+                cp_async16(reinterpret_cast<unsigned char*>(wtile + r * G::WSTR) + 16 * q,
+                           reinterpret_cast<const unsigned char*>(wsrc + (long long)(m0 + r) * a.ld + k0) + 16 * q);
+            }
+            constexpr int SP = KC / 2;
+            for (int e = tid; e < BM * SP; e += NT) {
+                int r = e / SP, q = e % SP;
+                cp_async16(stile + r * G::SSTR + 2 * q, a.sv + (long long)(m0 + r) * a.ld + k0 + 2 * q);
+            }
+        } else {
+            // rows k0..k0+KC of the data, columns m0..m0+BM
+            constexpr int WP = BM * (int)sizeof(WT) / 16;
+            for (int e = tid; e < KC * WP; e += NT) {
+                int r = e / WP, q = e % WP;
+                cp_async16(reinterpret_cast<unsigned char*>(wtile + r * G::WSTR) + 16 * q,
+                           reinterpret_cast<const unsigned char*>(wsrc + (long long)(k0 + r) * a.ld + m0) + 16 * q);
+            }
+            constexpr int SP = BM / 2;
+            for (int e = tid; e < KC * SP; e += NT) {
+                int r = e / SP, q = e % SP;
+                cp_async16(stile + r * G::SSTR + 2 * q, a.sv + (long long)(k0 + r) * a.ld + m0 + 2 * q);
+            }
+        }
+        // factor rows k0..k0+KC (contiguous KC*K doubles)
+        const double* fsrc = a.F + (long long)k0 * K;
+        for (int e = tid; e < (KC * K) / 2; e += NT) cp_async16(ftile + 2 * e, fsrc + 2 * e);
+    };
+
+    if (c_begin < c_end) load_chunk(0, c_begin);
+    cp_async_commit();
+
+    for (int c = c_begin; c < c_end; ++c) {
+        const int stg = (c - c_begin) & 1;
+        if (c + 1 < c_end) load_chunk(stg ^ 1, c + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        unsigned char* base = stage0 + stg * stage_bytes;
+        const WT* wtile = reinterpret_cast<const WT*>(base);
+        const double* stile = reinterpret_cast<const double*>(base + G::WBYTES);
+        const double* ftile = reinterpret_cast<const double*>(base + G::WBYTES + G::SBYTES);
+
+        // ---- generate the Z tile [KC][zw] from the factor tile
+        for (int k = warp; k < KC; k += NT / 32) {
+            const double* fr = ftile + k * K;
+#pragma unroll
+            for (int q = 0; q < CZ; ++q) {
+                int cc = lane + 32 * q;
+                if (cc < ncw) {
+                    int code = zcode[q];
+                    int ty = (unsigned)code >> 30;
+                    double v = 0.0;
+                    if (ty == 1) v = fr[(code >> 8) & 0xff] * fr[code & 0xff];
+                    else if (ty == 2) v = fr[(code >> 8) & 0xff];
+                    ztile[k * zw + cc] = v;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- DMMA over the chunk
+#pragma unroll 2
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            const int kl = kk * 4 + (lane & 3);
+            double aw[RT], as[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int ml = (wr * RT + r) * 8 + (lane >> 2);
+                if (!TRANS) {
+                    aw[r] = (double)wtile[ml * G::WSTR + kl];
+                    as[r] = stile[ml * G::SSTR + kl];
+                } else {
+                    aw[r] = (double)wtile[kl * G::WSTR + ml];
+                    as[r] = stile[kl * G::SSTR + ml];
+                }
+            }
+            const double* zrow = ztile + kl * zw + (lane >> 2);
+#pragma unroll
+            for (int ci = 0; ci < CTM; ++ci) {
+                const int ct = wc + ci * WC;
+                if (ct < nct) {
+                    const double b = zrow[ct * 8];
+                    const bool isz = ct < nct_z;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: packed lower triangle then the K linear terms
+    double* out = a.out + (long long)split * a.out_split_stride;
+    const int nco = L + K;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int m = m0 + (wr * RT + r) * 8 + (lane >> 2);
+        if (m < a.m_valid) {
+#pragma unroll
+            for (int ci = 0; ci < CTM; ++ci) {
+                const int ct = wc + ci * WC;
+                if (ct < nct) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int cc = ct * 8 + (lane & 3) * 2 + h;
+                        int oc = -1;
+                        if (ct < nct_z) { if (cc < L) oc = cc; }
+                        else { int cf = cc - nct_z * 8; if (cf < K) oc = L + cf; }
+                        if (oc >= 0) out[(long long)m * nco + oc] = acc[r][ci][h];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+static size_t stats_smem(int K, int zw) {
+    using G = TileGeom<TRANS, WT, BM, KC>;
+    size_t fbytes = ((size_t)(KC * K * 8) + 15) & ~(size_t)15;
+    return 2 * (G::WBYTES + G::SBYTES + fbytes) + (size_t)KC * zw * 8;
+}
+
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv, const double* F,
+                           long long ld, int m_valid, double* out, cudaStream_t st) {
+    StatsKArgs a;
+    a.wt = wt; a.sv = sv; a.F = F; a.out = out; a.ld = ld;
+    a.K = p.K; a.L = p.L; a.nct_z = p.nct_z; a.nct_f = p.nct_f; a.zw = p.zw;
+    a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
+    a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
+    auto kern = stats_kernel<BM, WR, WC, CTM, KC, TRANS, WT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    dim3 grid(p.mtiles, p.nsplit);
+    kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
+}
+
+// configuration table: cfg 0: K<=16 (BM=128, 8x1 warps, 19 col tiles, KC=32)
+//                      cfg 1: K<=32 (BM=32, 1x8 warps, 9x8 col tiles, KC=16)
+//                      cfg 2: K<=8  (BM=128, 8x1 warps, 6 col tiles, KC=32)
+#define BTF_CFG0 128, 8, 1, 19, 32
+#define BTF_CFG1 32, 1, 8, 9, 16
+#define BTF_CFG2 128, 8, 1, 6, 32
+
+bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad, int kdim_pad, int m_valid,
+                int nsplit_request, int sm_count) {
+    if (K < 1 || K > 32) return false;
+    p->K = K;
+    p->L = K * (K + 1) / 2;
+    p->nct_z = (p->L + 7) / 8;
+    p->nct_f = (K + 7) / 8;
+    int nct = p->nct_z + p->nct_f;
+    p->zw = (nct & 1) ? nct * 8 : nct * 8 + 8;
+    p->cfg = (nct <= 6) ? 2 : (nct <= 19 ? 0 : 1);
+    p->BM = (p->cfg == 1) ? 32 : 128;
+    p->KC = (p->cfg == 1) ? 16 : 32;
+    if (mdim_pad % p->BM || kdim_pad % p->KC) return false;
+    p->mtiles = mdim_pad / p->BM;
+    p->nchunks = kdim_pad / p->KC;
+    // split the contraction so the grid fills the machine in (nearly) whole waves
+    int ns = nsplit_request;
+    if (ns <= 0) {
+        ns = 1;
+        double best = -1.0;
+        int maxs = p->nchunks < 64 ? p->nchunks : 64;
+        for (int s = 1; s <= maxs; ++s) {
+            long long ctas = (long long)p->mtiles * s;
+            long long waves = (ctas + sm_count - 1) / sm_count;
+            double eff = (double)ctas / (double)(waves * sm_count);
+            // prefer few splits: demand a clear efficiency gain for more partial traffic
+            if (eff > best + 0.03) { best = eff; ns = s; }
+            if (best > 0.97) break;
+        }
+    }
+    if (ns > p->nchunks) ns = p->nchunks;
+    if (ns < 1) ns = 1;
+    p->chunks_per_split = (p->nchunks + ns - 1) / ns;
+    p->nsplit = (p->nchunks + p->chunks_per_split - 1) / p->chunks_per_split;
+    p->out_elems_per_split = (size_t)m_valid * (size_t)(p->L + K);
+#define SMEM_OF(...) (trans ? (weights_f64 ? stats_smem<__VA_ARGS__, true, double>(K, p->zw)   \
+                                           : stats_smem<__VA_ARGS__, true, uint8_t>(K, p->zw)) \
+                            : (weights_f64 ? stats_smem<__VA_ARGS__, false, double>(K, p->zw)  \
+                                           : stats_smem<__VA_ARGS__, false, uint8_t>(K, p->zw)))
+    if (p->cfg == 0) p->smem_bytes = SMEM_OF(BTF_CFG0);
+    else if (p->cfg == 1) p->smem_bytes = SMEM_OF(BTF_CFG1);
+    else p->smem_bytes = SMEM_OF(BTF_CFG2);
+#undef SMEM_OF
+    return p->smem_bytes <= 220 * 1024;
+}
+
+void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* wt, const double* sv,
+                  const double* F, long long ld, int m_valid, double* out, cudaStream_t st) {
+#define DISPATCH(...)                                                                                      \
+    do {                                                                                                   \
+        if (trans) {                                                                                       \
+            if (weights_f64) launch_stats_t<__VA_ARGS__, true, double>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_t<__VA_ARGS__, true, uint8_t>(p, wt, sv, F, ld, m_valid, out, st);           \
+        } else {                                                                                           \
+            if (weights_f64) launch_stats_t<__VA_ARGS__, false, double>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_t<__VA_ARGS__, false, uint8_t>(p, wt, sv, F, ld, m_valid, out, st);          \
+        }                                                                                                  \
+    } while (0)
+    if (p.cfg == 0) DISPATCH(BTF_CFG0);
+    else if (p.cfg == 1) DISPATCH(BTF_CFG1);
+    else DISPATCH(BTF_CFG2);
+#undef DISPATCH
+}
+
+// ------------------------------------------------------------------ nu2 residual (direct pass)
+// One block = 64 rows x 256 cells; partial = sum cnt*Mu^2 - 2*Mu*S over the block.
+template <int KMAX>
+__global__ void __launch_bounds__(256) residual_kernel(const uint8_t* __restrict__ cnt, const double* __restrict__ S,
+                                                       long long ld, const double* __restrict__ W,
+                                                       const double* __restrict__ V, int K,
+                                                       double* __restrict__ partials) {
+    __shared__ double ws[64 * KMAX];
+    __shared__ double sh[32];
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const int i0 = blockIdx.y * 64;
+    for (int e = threadIdx.x; e < 64 * K; e += 256) ws[e] = W[(long long)i0 * K + e];
+    double v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) v[k] = k < K ? V[(long long)p * K + k] : 0.0;
+    __syncthreads();
+    double accum = 0.0;
+    for (int r = 0; r < 64; ++r) {
+        long long o = (long long)(i0 + r) * ld + p;
+        double c = (double)cnt[o];
+        double s = S[o];
+        double mu = 0.0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) mu += ws[r * K + k] * v[k];
+        accum += mu * (c * mu - 2.0 * s);
+    }
+    double tot = block_sum(accum, sh);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+void launch_residual(const uint8_t* cnt, const double* S, long long ld, const double* W, const double* V,
+                     int nrows_pad, int Ppad, int K, double* partials, int* nblocks_out, cudaStream_t st) {
+    dim3 grid(Ppad / 256 > 0 ? Ppad / 256 : 1, nrows_pad / 64);
+    if (K <= 8) residual_kernel<8><<<grid, 256, 0, st>>>(cnt, S, ld, W, V, K, partials);
+    else if (K <= 16) residual_kernel<16><<<grid, 256, 0, st>>>(cnt, S, ld, W, V, K, partials);
+    else residual_kernel<32><<<grid, 256, 0, st>>>(cnt, S, ld, W, V, K, partials);
+    *nblocks_out = grid.x * grid.y;
+}
+
+}  // namespace btf
