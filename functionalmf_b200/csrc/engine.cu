@@ -262,7 +262,7 @@ int btf_create(const btf_config* c, btf_engine** out) {
 
     // workspaces
     CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->n * (e->kd + 1)));
-    CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->n));
+    CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->n * 2));
     e->partials_n = std::max<size_t>((size_t)(e->Ppad / 256) * (e->nloc_pad / 64), (size_t)2 * 148 * 16) + 64;
     CK(dev_alloc(&e->partials, e->partials_n));
     CK(dev_alloc(&e->lam_partials, e->M));
@@ -946,7 +946,7 @@ int btf_init_state(btf_engine* e, int32_t init_mask) {
         const bool tmp = e->Mloc < e->M;   // sharded engines own a smaller workspace
         if (tmp) {
             CK(cudaMalloc((void**)&wl, (size_t)e->M * e->n * (e->kd + 1) * sizeof(double)));
-            CK(cudaMalloc((void**)&wy, (size_t)e->M * e->n * sizeof(double)));
+            CK(cudaMalloc((void**)&wy, (size_t)e->M * e->n * 2 * sizeof(double)));
         }
         ba.work_L = tmp ? wl : e->work_L; ba.work_y = tmp ? wy : e->work_y;
         ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;

@@ -122,7 +122,8 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
     double* yw = Lw + (size_t)kd * LS;         // [kd] (+ chunk y/z: 2*kd)
     double* ychunk = yw + kd;                  // [kd]
     double* zchunk = ychunk + kd;              // [kd]
-    double* Ablk = zchunk + kd;                // [L+K]
+    double* dchunk = zchunk + kd;              // [kd]
+    double* Ablk = dchunk + kd;                // [L+K]
     double* Pband = Ablk + nco;                // [T][q+1]
     double* linv = Pband + (size_t)T * (q + 1);   // [RD]
     double* misc = linv + a.RD;                // [8]
@@ -140,7 +141,7 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
     }
 
     double* Lrow = a.work_L + (size_t)jl * n * LS;
-    double* yg = a.work_y + (size_t)jl * n;
+    double* yg = a.work_y + (size_t)jl * 2 * n;      // [y (n) | 1 / diag(L) (n)]
     const bool have_stats = a.stats != nullptr;     // nullptr: prior-only system (V initialisation)
     const double* stats0 = have_stats ? a.stats + (size_t)jg * T * nco : nullptr;
     const int mblk = tid / K;
@@ -181,49 +182,75 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
             }
             double s = 0.0, q0 = 0.0;
             bool valid = false;
-            const int cs0 = j - kd;
-            if (tid <= kd) {
-                const int i = j + tid;
-                if (i < n) {
+            // Dot products over the window columns c in [cs, j): column c lives in slot c % kd
+            // and consecutive columns are kd doubles apart (slot + 1, offset - 1), so the
+            // range splits into at most two contiguous runs; four independent accumulators
+            // keep the shared-memory loads and DFMAs pipelined.
+            if (tid <= kd + 1) {
+                const bool rhs = tid == kd + 1;
+                const int off = rhs ? 0 : tid;
+                const int i = j + off;
+                if (rhs || i < n) {
                     valid = true;
-                    if (k + tid < K) q0 = Ablk[tri(k + tid, k)];
-                    if (on_kdiag && t + mblk < T) q0 += Pband[t * (q + 1) + mblk];
-                    if (tid == 0) q0 += jitter;
-                    s = q0;
-                    int c = cs0 + tid; if (c < 0) c = 0;
-                    int slot = c % kd;
-                    for (; c < j; ++c) {
-                        const double* col = Lw + slot * LS + (j - c);
-                        s -= col[tid] * col[0];
-                        if (++slot == kd) slot = 0;
+                    if (rhs) {
+                        q0 = Ablk[L + k];
+                    } else {
+                        if (k + tid < K) q0 = Ablk[tri(k + tid, k)];
+                        if (on_kdiag && t + mblk < T) q0 += Pband[t * (q + 1) + mblk];
+                        if (tid == 0) q0 += jitter;
                     }
-                }
-            } else if (tid == kd + 1) {
-                s = Ablk[L + k];
-                int c = cs0 < 0 ? 0 : cs0;
-                int slot = c % kd;
-                for (; c < j; ++c) {
-                    s -= Lw[slot * LS + (j - c)] * yw[slot];
-                    if (++slot == kd) slot = 0;
+                    int cs = j - kd + off; if (cs < 0) cs = 0;
+                    int len = j - cs;
+                    int s0 = cs % kd;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 1
+                    for (int seg = 0; seg < 2 && len > 0; ++seg) {
+                        const int run = min(len, kd - s0);
+                        const double* pl = Lw + s0 * LS + (j - cs);       // L[j][c] at pl[0], L[i][c] at pl[tid]
+                        const double* py = yw + s0;
+                        int x = 0;
+                        if (!rhs) {
+                            for (; x + 4 <= run; x += 4) {
+                                a0 += pl[off] * pl[0];
+                                a1 += pl[kd + off] * pl[kd];
+                                a2 += pl[2 * kd + off] * pl[2 * kd];
+                                a3 += pl[3 * kd + off] * pl[3 * kd];
+                                pl += 4 * kd;
+                            }
+                            for (; x < run; ++x) { a0 += pl[off] * pl[0]; pl += kd; }
+                        } else {
+                            for (; x + 4 <= run; x += 4) {
+                                a0 += pl[0] * py[x];
+                                a1 += pl[kd] * py[x + 1];
+                                a2 += pl[2 * kd] * py[x + 2];
+                                a3 += pl[3 * kd] * py[x + 3];
+                                pl += 4 * kd;
+                            }
+                            for (; x < run; ++x) { a0 += pl[0] * py[x]; pl += kd; }
+                        }
+                        cs += run; len -= run; s0 = 0;
+                    }
+                    s = q0 - ((a0 + a1) + (a2 + a3));
                 }
             }
             if (tid == 0) {
                 if (!(s > 0.0) || isinf(s)) fail_flag = 1;
-                else misc[0] = sqrt(s);
+                else { const double lj = sqrt(s); misc[0] = lj; misc[1] = 1.0 / lj; }
             }
             __syncthreads();
             if (fail_flag) { broke = true; break; }
-            const double ljj = misc[0];
+            const double ljj = misc[0], rinv = misc[1];
             const int slot_j = j % kd;
             if (tid <= kd) {
-                double val = tid == 0 ? ljj : (valid ? s / ljj : 0.0);
+                double val = tid == 0 ? ljj : (valid ? s * rinv : 0.0);
                 Lw[slot_j * LS + tid] = val;
                 if (valid) {
                     Lrow[(size_t)(j + tid) * LS + kd - tid] = val;
                     if (a.diag_band) a.diag_band[((size_t)jl * n + j + tid) * LS + kd - tid] = q0;
                 }
+                if (tid == 0) yg[n + j] = rinv;
             } else if (tid == kd + 1) {
-                double yj = s / ljj;
+                double yj = s * rinv;
                 yw[slot_j] = yj;
                 yg[j] = yj;
             }
@@ -279,13 +306,14 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
         for (int e = tid; e < cnt; e += NT) {
             int i = lo - NB + e;
             if (i >= 0) { double yv = yg[i]; ychunk[e] = yv; zchunk[e] = noise(i); }
+            dchunk[e] = yg[n + lo + e];
         }
         __syncthreads();
         for (int j = jc; j >= lo; --j) {
             const int jj = j - lo;
             if (tid < NB && myrow == j) {
-                const double ljj = Lc[jj * LS + kd];
-                const double xm = wm / ljj, xd = wd / ljj;
+                const double rj = dchunk[jj];
+                const double xm = wm * rj, xd = wd * rj;
                 xs[par * 2] = xm; xs[par * 2 + 1] = xd;
                 Vout[j] = xd;
                 if (a.diag_mean) a.diag_mean[(size_t)jg * n + j] = xm;
@@ -309,21 +337,24 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
     // ---- nu2 by-product: sum_t v_t^T A_t v_t - 2 v_t . b_t with the UNSCALED statistics
     if (a.resid_partials && have_stats) {
         double accum = 0.0;
-        for (int t = 0; t < T; ++t) {
-            const double* sb = stats0 + (size_t)t * nco;
-            const double* v = Vout + (size_t)t * K;
-            for (int c = tid; c < nco; c += NT) {
+        for (int c = tid; c < nco; c += NT) {
+            int k1 = 0, k2 = 0;
+            double wgt = -2.0;
+            if (c < L) {
+                k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
+                while (k1 * (k1 + 1) / 2 > c) --k1;
+                while ((k1 + 1) * (k1 + 2) / 2 <= c) ++k1;
+                k2 = c - k1 * (k1 + 1) / 2;
+                wgt = k1 == k2 ? 1.0 : 2.0;
+            } else {
+                k1 = c - L;
+            }
+            for (int t = 0; t < T; ++t) {
+                const double* sb = stats0 + (size_t)t * nco + c;
+                const double* v = Vout + (size_t)t * K;
                 double sv = 0.0;
-                for (int s = 0; s < a.nsplit; ++s) sv += sb[s * a.split_stride + c];
-                if (c < L) {
-                    int k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
-                    while (k1 * (k1 + 1) / 2 > c) --k1;
-                    while ((k1 + 1) * (k1 + 2) / 2 <= c) ++k1;
-                    int k2 = c - k1 * (k1 + 1) / 2;
-                    accum += (k1 == k2 ? 1.0 : 2.0) * sv * v[k1] * v[k2];
-                } else {
-                    accum -= 2.0 * sv * v[c - L];
-                }
+                for (int s = 0; s < a.nsplit; ++s) sv += sb[s * a.split_stride];
+                accum += wgt * sv * v[k1] * (c < L ? v[k2] : 1.0);
             }
         }
         double tot = block_sum(accum, misc + 8);
@@ -336,7 +367,7 @@ void launch_band_solve(const BandSolveArgs& a, cudaStream_t st) {
     int nt = ((kd + 2 + 31) / 32) * 32;
     int nt2 = (((nco + 3) / 4 + 31) / 32) * 32;
     if (nt2 > nt) nt = nt2;
-    size_t smem = ((size_t)kd * (kd + 1) + 3 * (size_t)kd + nco + (size_t)a.T * (q + 1) + a.RD + 8 + 40) * sizeof(double);
+    size_t smem = ((size_t)kd * (kd + 1) + 4 * (size_t)kd + nco + (size_t)a.T * (q + 1) + a.RD + 8 + 40) * sizeof(double);
     static size_t max_set = 0;
     if (smem > 48 * 1024 && smem > max_set) {
         cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

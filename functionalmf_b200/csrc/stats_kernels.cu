@@ -17,6 +17,7 @@
 // kind, so this is the B200 FP64 tensor path.
 #include "kernels.h"
 #include <stdio.h>
+#include <algorithm>
 
 namespace btf {
 
@@ -122,25 +123,39 @@ struct StatsKArgs {
 
 template <bool TRANS, typename WT, int BM, int KC>
 struct TileGeom {
-    // shared-memory row strides (elements) chosen so that the DMMA fragment reads
-    // are bank-conflict free and every cp.async destination is 16-byte aligned
+    // Shared-memory row strides (elements).  A 64-bit LDS is served per half-warp, so
+    // the four k-rows (or four m-rows) a half-warp touches must fall into disjoint
+    // 8-word bank groups: double strides are = 4 (mod 16); byte tiles use strides whose
+    // word offsets are distinct.  Every cp.async destination stays 16-byte aligned.
     static constexpr int WROWS = TRANS ? KC : BM;
-    static constexpr int WSTR = sizeof(WT) == 1 ? (TRANS ? BM + 16 : 48) : (TRANS ? BM + 8 : KC + 4);
-    static constexpr int SSTR = TRANS ? BM + 8 : KC + 4;
+    static constexpr int WSTR = sizeof(WT) == 1 ? (TRANS ? BM + 16 : 48) : (TRANS ? BM + 4 : KC + 4);
+    static constexpr int SSTR = TRANS ? BM + 4 : KC + 4;
     static constexpr int WBYTES = WROWS * WSTR * (int)sizeof(WT);
     static constexpr int SBYTES = WROWS * SSTR * 8;
 };
 
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Column tiles (8 generated columns each): nct_z tiles of packed products, then nct_f
+// tiles of plain factor columns.  Warp column-group wc owns product tiles
+// [wc*ZPW, (wc+1)*ZPW) and factor tiles [wc*FPW, (wc+1)*FPW).  With KFIX > 0 all of this
+// is compile-time: the inner loop has no branches and out-of-range tile slots compute
+// into accumulators that are never stored.
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
 __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
     constexpr int NT = 32 * WR * WC;
     constexpr int RT = BM / 8 / WR;
-    constexpr int CZ = (CTM * WC * 8 + 31) / 32;
+    constexpr bool FIX = KFIX > 0;
     using G = TileGeom<TRANS, WT, BM, KC>;
     extern __shared__ __align__(16) unsigned char smem[];
 
-    const int K = a.K, L = a.L, nct_z = a.nct_z, nct = a.nct_z + a.nct_f, zw = a.zw;
-    const int ncw = nct * 8;
+    const int K = FIX ? KFIX : a.K;
+    const int L = K * (K + 1) / 2;
+    const int nct_z = cdiv(L, 8), nct_f = cdiv(K, 8);
+    const int ZPW = cdiv(nct_z, WC), FPW = cdiv(nct_f, WC);     // ZPW + FPW <= CTM (checked on the host)
+    const int zw = a.zw;
+    const int ncw = (nct_z + nct_f) * 8;
+    constexpr int CZ = FIX ? cdiv((cdiv(KFIX * (KFIX + 1) / 2, 8) + cdiv(KFIX, 8)) * 8, 32) : cdiv(CTM * WC * 8, 32);
     const int fbytes = ((KC * K * 8) + 15) & ~15;
     const int stage_bytes = G::WBYTES + G::SBYTES + fbytes;
     unsigned char* stage0 = smem;
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
     const int c_end = min(a.nchunks, c_begin + a.chunks_per_split);
 
     // which generated column(s) this lane fills during Z generation
-    // code: bit31..30 type (0 zero, 1 product, 2 copy), k1 = bits 8..15, k2 = bits 0..7
+    // code: bits 31..30 type (0 zero, 1 product, 2 copy), k1 = bits 8..15, k2 = bits 0..7
     int zcode[CZ];
 #pragma unroll
     for (int q = 0; q < CZ; ++q) {
@@ -222,6 +237,10 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
         for (int e = tid; e < (KC * K) / 2; e += NT) cp_async16(ftile + 2 * e, fsrc + 2 * e);
     };
 
+    // per-warp column offsets of the tile slots inside a Z row
+    const int zoff_z = wc * ZPW * 8 + (lane >> 2);
+    const int zoff_f = (nct_z + wc * FPW) * 8 + (lane >> 2);
+
     if (c_begin < c_end) load_chunk(0, c_begin);
     cp_async_commit();
 
@@ -271,15 +290,26 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
                     as[r] = stile[kl * G::SSTR + ml];
                 }
             }
-            const double* zrow = ztile + kl * zw + (lane >> 2);
+            const double* zrow = ztile + kl * zw;
+            if (FIX) {
 #pragma unroll
-            for (int ci = 0; ci < CTM; ++ci) {
-                const int ct = wc + ci * WC;
-                if (ct < nct) {
-                    const double b = zrow[ct * 8];
-                    const bool isz = ct < nct_z;
+                for (int ci = 0; ci < CTM; ++ci) {
+                    // compile-time operand choice: the first ZPW slots are product tiles
+                    const bool isz = ci < ZPW;
+                    const double b = isz ? zrow[zoff_z + ci * 8] : zrow[zoff_f + (ci - ZPW) * 8];
 #pragma unroll
                     for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < CTM; ++ci) {
+                    const bool isz = ci < ZPW;
+                    const int tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
+                    if (ci < ZPW + FPW && tl < (isz ? nct_z : nct_f)) {
+                        const double b = isz ? zrow[zoff_z + ci * 8] : zrow[zoff_f + (ci - ZPW) * 8];
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+                    }
                 }
             }
         }
@@ -296,14 +326,15 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
         if (m < a.m_valid) {
 #pragma unroll
             for (int ci = 0; ci < CTM; ++ci) {
-                const int ct = wc + ci * WC;
-                if (ct < nct) {
+                const bool isz = ci < ZPW;
+                const int tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
+                if (ci < ZPW + FPW && tl < (isz ? nct_z : nct_f)) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        int cc = ct * 8 + (lane & 3) * 2 + h;
+                        const int cc = tl * 8 + (lane & 3) * 2 + h;
                         int oc = -1;
-                        if (ct < nct_z) { if (cc < L) oc = cc; }
-                        else { int cf = cc - nct_z * 8; if (cf < K) oc = L + cf; }
+                        if (isz) { if (cc < L) oc = cc; }
+                        else if (cc < K) oc = L + cc;
                         if (oc >= 0) out[(long long)m * nco + oc] = acc[r][ci][h];
                     }
                 }
@@ -319,7 +350,7 @@ static size_t stats_smem(int K, int zw) {
     return 2 * (G::WBYTES + G::SBYTES + fbytes) + (size_t)KC * zw * 8;
 }
 
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
 static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv, const double* F,
                            long long ld, int m_valid, double* out, cudaStream_t st) {
     StatsKArgs a;
@@ -327,7 +358,7 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     a.K = p.K; a.L = p.L; a.nct_z = p.nct_z; a.nct_f = p.nct_f; a.zw = p.zw;
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
-    auto kern = stats_kernel<BM, WR, WC, CTM, KC, TRANS, WT>;
+    auto kern = stats_kernel<BM, WR, WC, CTM, KC, TRANS, WT, KFIX>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -337,12 +368,21 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
 
-// configuration table: cfg 0: K<=16 (BM=128, 8x1 warps, 19 col tiles, KC=32)
-//                      cfg 1: K<=32 (BM=32, 1x8 warps, 9x8 col tiles, KC=16)
-//                      cfg 2: K<=8  (BM=128, 8x1 warps, 6 col tiles, KC=32)
+// Tile configurations  (BM, WR, WC, CTM, KC):
+//   cfg 0: generic K <= 16   128 rows, 8x1 warps, 19 column-tile slots, KC 32
+//   cfg 1: generic K <= 32    32 rows, 1x8 warps, 10 slots per warp,    KC 16
+//   cfg 2: generic K <=  8   128 rows, 8x1 warps,  6 slots,             KC 32
+//   cfg 3: K == 16 (compile-time) 128 rows, 4x2 warps, 9+1 slots per warp, KC 32
+//   cfg 4: K == 32 (compile-time)  32 rows, 1x8 warps, 9+1 slots per warp, KC 16
+//   cfg 5: K ==  8 (compile-time) 128 rows, 8x1 warps, 5+1 slots,          KC 32
 #define BTF_CFG0 128, 8, 1, 19, 32
-#define BTF_CFG1 32, 1, 8, 9, 16
+#define BTF_CFG1 32, 1, 8, 10, 16
 #define BTF_CFG2 128, 8, 1, 6, 32
+#define BTF_CFG3 128, 4, 2, 10, 32
+#define BTF_CFG4 32, 1, 8, 10, 16
+#define BTF_CFG5 128, 8, 1, 6, 32
+
+static int cfg_wc(int cfg) { return (cfg == 1 || cfg == 4) ? 8 : (cfg == 3 ? 2 : 1); }
 
 bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad, int kdim_pad, int m_valid,
                 int nsplit_request, int sm_count) {
@@ -351,11 +391,19 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
     p->L = K * (K + 1) / 2;
     p->nct_z = (p->L + 7) / 8;
     p->nct_f = (K + 7) / 8;
-    int nct = p->nct_z + p->nct_f;
-    p->zw = (nct & 1) ? nct * 8 : nct * 8 + 8;
-    p->cfg = (nct <= 6) ? 2 : (nct <= 19 ? 0 : 1);
-    p->BM = (p->cfg == 1) ? 32 : 128;
-    p->KC = (p->cfg == 1) ? 16 : 32;
+    const int nct = p->nct_z + p->nct_f;
+    if (K == 16) p->cfg = 3;
+    else if (K == 32) p->cfg = 4;
+    else if (K == 8) p->cfg = 5;
+    else p->cfg = (nct <= 6) ? 2 : (nct <= 19 ? 0 : 1);
+    const int WC = cfg_wc(p->cfg);
+    // Z row width: every tile slot any warp may touch, rounded so that zw = 4 or 12 (mod 16)
+    int need = std::max(nct, std::max(WC * cdiv(p->nct_z, WC), p->nct_z + WC * cdiv(p->nct_f, WC))) * 8;
+    int zw = need;
+    while (!((zw % 16) == 4 || (zw % 16) == 12)) ++zw;
+    p->zw = zw;
+    p->BM = (p->cfg == 1 || p->cfg == 4) ? 32 : 128;
+    p->KC = (p->cfg == 1 || p->cfg == 4) ? 16 : 32;
     if (mdim_pad % p->BM || kdim_pad % p->KC) return false;
     p->mtiles = mdim_pad / p->BM;
     p->nchunks = kdim_pad / p->KC;
@@ -383,28 +431,38 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
                                            : stats_smem<__VA_ARGS__, true, uint8_t>(K, p->zw)) \
                             : (weights_f64 ? stats_smem<__VA_ARGS__, false, double>(K, p->zw)  \
                                            : stats_smem<__VA_ARGS__, false, uint8_t>(K, p->zw)))
-    if (p->cfg == 0) p->smem_bytes = SMEM_OF(BTF_CFG0);
-    else if (p->cfg == 1) p->smem_bytes = SMEM_OF(BTF_CFG1);
-    else p->smem_bytes = SMEM_OF(BTF_CFG2);
+    switch (p->cfg) {
+        case 0: p->smem_bytes = SMEM_OF(BTF_CFG0); break;
+        case 1: p->smem_bytes = SMEM_OF(BTF_CFG1); break;
+        case 2: p->smem_bytes = SMEM_OF(BTF_CFG2); break;
+        case 3: p->smem_bytes = SMEM_OF(BTF_CFG3); break;
+        case 4: p->smem_bytes = SMEM_OF(BTF_CFG4); break;
+        default: p->smem_bytes = SMEM_OF(BTF_CFG5); break;
+    }
 #undef SMEM_OF
     return p->smem_bytes <= 220 * 1024;
 }
 
 void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* wt, const double* sv,
                   const double* F, long long ld, int m_valid, double* out, cudaStream_t st) {
-#define DISPATCH(...)                                                                                      \
-    do {                                                                                                   \
-        if (trans) {                                                                                       \
-            if (weights_f64) launch_stats_t<__VA_ARGS__, true, double>(p, wt, sv, F, ld, m_valid, out, st); \
-            else launch_stats_t<__VA_ARGS__, true, uint8_t>(p, wt, sv, F, ld, m_valid, out, st);           \
-        } else {                                                                                           \
-            if (weights_f64) launch_stats_t<__VA_ARGS__, false, double>(p, wt, sv, F, ld, m_valid, out, st); \
-            else launch_stats_t<__VA_ARGS__, false, uint8_t>(p, wt, sv, F, ld, m_valid, out, st);          \
-        }                                                                                                  \
+#define DISPATCH(KF, ...)                                                                                        \
+    do {                                                                                                         \
+        if (trans) {                                                                                             \
+            if (weights_f64) launch_stats_t<__VA_ARGS__, true, double, KF>(p, wt, sv, F, ld, m_valid, out, st);  \
+            else launch_stats_t<__VA_ARGS__, true, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);             \
+        } else {                                                                                                 \
+            if (weights_f64) launch_stats_t<__VA_ARGS__, false, double, KF>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
+        }                                                                                                        \
     } while (0)
-    if (p.cfg == 0) DISPATCH(BTF_CFG0);
-    else if (p.cfg == 1) DISPATCH(BTF_CFG1);
-    else DISPATCH(BTF_CFG2);
+    switch (p.cfg) {
+        case 0: DISPATCH(0, BTF_CFG0); break;
+        case 1: DISPATCH(0, BTF_CFG1); break;
+        case 2: DISPATCH(0, BTF_CFG2); break;
+        case 3: DISPATCH(16, BTF_CFG3); break;
+        case 4: DISPATCH(32, BTF_CFG4); break;
+        default: DISPATCH(8, BTF_CFG5); break;
+    }
 #undef DISPATCH
 }
 
