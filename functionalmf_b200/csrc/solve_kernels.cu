@@ -199,25 +199,35 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
                         if (on_kdiag && t + mblk < T) q0 += Pband[t * (q + 1) + mblk];
                         if (tid == 0) q0 += jitter;
                     }
-                    int cs = j - kd + off; if (cs < 0) cs = 0;
-                    int len = j - cs;
-                    int s0 = cs % kd;
+                    // All threads walk the SAME window columns c = cbeg .. j-1 in lock step, so
+                    // L[j][c] is a shared-memory broadcast and L[i][c] is a unit-stride read
+                    // (thread-private start columns would put every lane on one bank).  Row
+                    // i = j + off only couples to columns with (j - c) + off <= kd.
+                    int cbeg = j - kd; if (cbeg < 0) cbeg = 0;
+                    int len = j - cbeg;
+                    int s0 = cbeg % kd;
+                    int o = j - cbeg;                      // offset of L[j][c] inside its slot row
+                    const int lim = kd - off;              // active while o <= lim
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 1
                     for (int seg = 0; seg < 2 && len > 0; ++seg) {
                         const int run = min(len, kd - s0);
-                        const double* pl = Lw + s0 * LS + (j - cs);       // L[j][c] at pl[0], L[i][c] at pl[tid]
+                        const double* pl = Lw + s0 * LS + o;              // L[j][c] at pl[0], L[i][c] at pl[off]
                         const double* py = yw + s0;
                         int x = 0;
                         if (!rhs) {
                             for (; x + 4 <= run; x += 4) {
-                                a0 += pl[off] * pl[0];
-                                a1 += pl[kd + off] * pl[kd];
-                                a2 += pl[2 * kd + off] * pl[2 * kd];
-                                a3 += pl[3 * kd + off] * pl[3 * kd];
+                                const double l0 = (o - x <= lim) ? pl[off] : 0.0;
+                                const double l1 = (o - x - 1 <= lim) ? pl[kd + off] : 0.0;
+                                const double l2 = (o - x - 2 <= lim) ? pl[2 * kd + off] : 0.0;
+                                const double l3 = (o - x - 3 <= lim) ? pl[3 * kd + off] : 0.0;
+                                a0 += l0 * pl[0];
+                                a1 += l1 * pl[kd];
+                                a2 += l2 * pl[2 * kd];
+                                a3 += l3 * pl[3 * kd];
                                 pl += 4 * kd;
                             }
-                            for (; x < run; ++x) { a0 += pl[off] * pl[0]; pl += kd; }
+                            for (; x < run; ++x) { if (o - x <= lim) a0 += pl[off] * pl[0]; pl += kd; }
                         } else {
                             for (; x + 4 <= run; x += 4) {
                                 a0 += pl[0] * py[x];
@@ -228,7 +238,7 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
                             }
                             for (; x < run; ++x) { a0 += pl[0] * py[x]; pl += kd; }
                         }
-                        cs += run; len -= run; s0 = 0;
+                        o -= run; len -= run; s0 = 0;
                     }
                     s = q0 - ((a0 + a1) + (a2 + a3));
                 }
