@@ -153,13 +153,18 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
 
     while (true) {
         // ---- factorisation + forward substitution
-        double pre[4];
+        // statistics of block t+1 are fetched while block t is being factorised: the raw loads
+        // (two split partials) stay in registers and are only combined at the next block boundary
+        double preA[4], preB[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             int c = tid + u * NT;
-            double v = 0.0;
-            if (c < nco && have_stats) for (int s = 0; s < a.nsplit; ++s) v += stats0[s * a.split_stride + c];
-            pre[u] = v * scale;
+            preA[u] = 0.0; preB[u] = 0.0;
+            if (c < nco && have_stats) {
+                preA[u] = stats0[c];
+                if (a.nsplit > 1) preB[u] = stats0[a.split_stride + c];
+                for (int s = 2; s < a.nsplit; ++s) preA[u] += stats0[s * a.split_stride + c];
+            }
         }
         __syncthreads();
         int t = 0, k = 0;
@@ -167,16 +172,18 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
         for (int j = 0; j < n; ++j) {
             if (k == 0) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { int c = tid + u * NT; if (c < nco) Ablk[c] = pre[u]; }
+                for (int u = 0; u < 4; ++u) { int c = tid + u * NT; if (c < nco) Ablk[c] = (preA[u] + preB[u]) * scale; }
                 __syncthreads();
                 if (t + 1 < T && have_stats) {
                     const double* nx = stats0 + (size_t)(t + 1) * nco;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         int c = tid + u * NT;
-                        double v = 0.0;
-                        if (c < nco) for (int s = 0; s < a.nsplit; ++s) v += nx[s * a.split_stride + c];
-                        pre[u] = v * scale;
+                        if (c < nco) {
+                            preA[u] = nx[c];
+                            preB[u] = a.nsplit > 1 ? nx[a.split_stride + c] : 0.0;
+                            for (int s = 2; s < a.nsplit; ++s) preA[u] += nx[s * a.split_stride + c];
+                        }
                     }
                 }
             }
@@ -312,7 +319,17 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
         const int lo = jc - kd + 1 < 0 ? 0 : jc - kd + 1;
         const int cnt = jc - lo + 1;
         __syncthreads();
-        for (int e = tid; e < cnt * LS; e += NT) Lc[e] = Lrow[(size_t)lo * LS + e];
+        {   // batched global -> shared copy of the chunk (8 independent loads in flight per thread)
+            const double* src = Lrow + (size_t)lo * LS;
+            const int total = cnt * LS;
+            for (int base = tid; base < total; base += NT * 8) {
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { int e = base + u * NT; r8[u] = e < total ? src[e] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { int e = base + u * NT; if (e < total) Lc[e] = r8[u]; }
+            }
+        }
         for (int e = tid; e < cnt; e += NT) {
             int i = lo - NB + e;
             if (i >= 0) { double yv = yg[i]; ychunk[e] = yv; zchunk[e] = noise(i); }
