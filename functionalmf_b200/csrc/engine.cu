@@ -261,7 +261,7 @@ int btf_create(const btf_config* c, btf_engine** out) {
     CK(dev_alloc(&e->col_stats, e->plan_col.nsplit * e->plan_col.out_elems_per_split));
 
     // workspaces
-    CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->n * (e->kd + 1)));
+    CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->n * (e->kd + e->K + 1)));
     CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->n * 2));
     e->partials_n = std::max<size_t>((size_t)(e->Ppad / 256) * (e->nloc_pad / 64), (size_t)2 * 148 * 16) + 64;
     CK(dev_alloc(&e->partials, e->partials_n));
@@ -945,7 +945,7 @@ int btf_init_state(btf_engine* e, int32_t init_mask) {
         double *wl = nullptr, *wy = nullptr;
         const bool tmp = e->Mloc < e->M;   // sharded engines own a smaller workspace
         if (tmp) {
-            CK(cudaMalloc((void**)&wl, (size_t)e->M * e->n * (e->kd + 1) * sizeof(double)));
+            CK(cudaMalloc((void**)&wl, (size_t)e->M * e->n * (e->kd + e->K + 1) * sizeof(double)));
             CK(cudaMalloc((void**)&wy, (size_t)e->M * e->n * 2 * sizeof(double)));
         }
         ba.work_L = tmp ? wl : e->work_L; ba.work_y = tmp ? wy : e->work_y;

@@ -65,13 +65,15 @@ struct BandSolveArgs {
     double* V;             // [M][T][K]
     const double* z_inject;   // [M][T][K] or nullptr
     uint64_t seed;
-    double* work_L;        // [ncols_loc][n][kd+1]
-    double* work_y;        // [ncols_loc][n]
+    double* work_L;        // [ncols_loc][n][kd+K+1]  (scalar kernel uses the first n*(kd+1) of each)
+    double* work_y;        // [ncols_loc][2n]  y | 1/diag(L)
     int force_psd, attempts; double eps;
     double *diag_band, *diag_chol, *diag_mean; int* diag_retries;
     double* resid_partials;   // [ncols_loc]: sum_t v^T A v - 2 v.b   (nu2 by-product)
 };
 void launch_band_solve(const BandSolveArgs& a, cudaStream_t st);
+// blocked (DMMA) variant for K in {8,16,32}; returns false when the shape has no instantiation
+bool launch_band_solve_blocked(const BandSolveArgs& a, cudaStream_t st);
 
 // ---------------------------------------------------------------- K5 hyper-parameters
 struct HyperArgs {

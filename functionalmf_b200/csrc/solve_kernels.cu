@@ -5,6 +5,7 @@
 //      kron/SpGEMM assembly of factor.py:396-408: the band is assembled on the fly
 //      from the per-(j,t) statistics and the trend-filtering stencils).
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace btf {
 
@@ -140,7 +141,7 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
         Pband[e] = s;
     }
 
-    double* Lrow = a.work_L + (size_t)jl * n * LS;
+    double* Lrow = a.work_L + (size_t)jl * n * (kd + K + 1);
     double* yg = a.work_y + (size_t)jl * 2 * n;      // [y (n) | 1 / diag(L) (n)]
     const bool have_stats = a.stats != nullptr;     // nullptr: prior-only system (V initialisation)
     const double* stats0 = have_stats ? a.stats + (size_t)jg * T * nco : nullptr;
@@ -390,6 +391,8 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
 }
 
 void launch_band_solve(const BandSolveArgs& a, cudaStream_t st) {
+    static const bool force_scalar = getenv("BTF_BAND_SCALAR") != nullptr;
+    if (!force_scalar && launch_band_solve_blocked(a, st)) return;
     const int q = a.order + 1, kd = q * a.K, L = a.K * (a.K + 1) / 2, nco = L + a.K;
     int nt = ((kd + 2 + 31) / 32) * 32;
     int nt2 = (((nco + 3) / 4 + 31) / 32) * 32;
