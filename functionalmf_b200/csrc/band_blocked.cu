@@ -45,8 +45,9 @@ struct BlkGeom {
     static constexpr int BLK = KB * KS;
     static constexpr int NBLK = (Q + 1) * (Q + 2) / 2;
     static constexpr int ROWS = Q * KB + 1;                // trsm rows (+1: right-hand side)
-    static constexpr int NTMIN = KB >= 16 ? 128 : 64;
+    static constexpr int NTMIN = KB > 16 ? 128 : 64;       // small CTAs: all columns resident in one wave
     static constexpr int NT = (ROWS > NTMIN ? (ROWS + 31) / 32 * 32 : NTMIN);
+    static constexpr int MINB = KB > 16 ? 2 : 65536 / (128 * NT);   // residency target: <= 128 registers per thread for KB <= 16
     static constexpr int KK = KB * KB;                     // unpadded block (global layout)
     // the backward double buffer [2][(Q+1) KK] aliases the window region
     static constexpr int WREG = NBLK * BLK > 2 * (Q + 1) * KK ? NBLK * BLK : 2 * (Q + 1) * KK;
@@ -57,7 +58,7 @@ struct BlkGeom {
 }  // namespace
 
 template <int KB, int Q>
-__global__ void __launch_bounds__(BlkGeom<KB, Q>::NT) band_blocked_kernel(BandSolveArgs a) {
+__global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band_blocked_kernel(BandSolveArgs a) {
     using G = BlkGeom<KB, Q>;
     constexpr int KS = G::KS, BLK = G::BLK, NT = G::NT, KK = G::KK;
     constexpr int L = KB * (KB + 1) / 2, nco = L + KB, kd = Q * KB, LS = kd + 1;
@@ -75,12 +76,17 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT) band_blocked_kernel(BandSo
     double* Pband = xw + 2 * (Q + 1) * KB;             // [T][Q+1]
     double* linv = Pband + (size_t)T * (Q + 1);        // [RD]
     double* red = linv + a.RD;                         // [40]
+    unsigned short* pairtab = reinterpret_cast<unsigned short*>(red + 40);   // [L] packed index -> (i << 8 | c)
     __shared__ int fail_flag;
 
     const double scale = a.homoskedastic ? 1.0 / a.scal->nu2 : 1.0;
     const double lam2 = a.scal->lam2;
     for (int r = tid; r < a.RD; r += NT) linv[r] = 1.0 / (lam2 * a.Tau2[(size_t)jg * a.RD + r]);
     if (tid == 0) fail_flag = 0;
+    for (int e = tid; e < KB * KB; e += NT) {
+        const int i = e / KB, c = e % KB;
+        if (c <= i) pairtab[tri(i, c)] = (unsigned short)((i << 8) | c);
+    }
     __syncthreads();
     for (int e = tid; e < T * (Q + 1); e += NT) {
         double s = 0.0;
@@ -105,18 +111,18 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT) band_blocked_kernel(BandSo
         const double* sb = have_stats ? stats0 + (size_t)arow * nco : nullptr;
         double* D = Wb + G::slot(arow, 0) * BLK;
         const double pd = Pband[arow * (Q + 1)] + jitter;
-        for (int e = t0; e < KB * KB; e += nthreads) {
-            const int i = e / KB, c = e % KB;
+        // only the lower triangle is ever read: stream the packed statistics contiguously
+#pragma unroll 4
+        for (int e = t0; e < L; e += nthreads) {
+            const int i = pairtab[e] >> 8, c = pairtab[e] & 0xff;
             double v = 0.0;
-            if (c <= i) {
-                if (have_stats) {
-                    double sv = sb[tri(i, c)];
-                    for (int s = 1; s < a.nsplit; ++s) sv += sb[s * a.split_stride + tri(i, c)];
-                    v = sv * scale;
-                }
-                if (c == i) v += pd;
-                if (a.diag_band) a.diag_band[((size_t)jl * n + arow * KB + i) * LS + kd - (i - c)] = v;
+            if (have_stats) {
+                double sv = sb[e];
+                for (int s = 1; s < a.nsplit; ++s) sv += sb[s * a.split_stride + e];
+                v = sv * scale;
             }
+            if (c == i) v += pd;
+            if (a.diag_band) a.diag_band[((size_t)jl * n + arow * KB + i) * LS + kd - (i - c)] = v;
             D[i * KS + c] = v;
         }
         for (int e = t0; e < KB; e += nthreads) {
@@ -161,8 +167,8 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT) band_blocked_kernel(BandSo
                 for (int j = 0; j < KB; ++j) {
                     const double d = __shfl_sync(full, ar[j], j);
                     if (!(d > 0.0) || isinf(d)) ok = false;
-                    const double ljj = sqrt(ok ? d : 1.0);
-                    const double rinv = 1.0 / ljj;
+                    const double rinv = rsqrt(ok ? d : 1.0);      // shortens the serial pivot chain
+                    const double ljj = d * rinv;
                     const double lij = (lane == j) ? ljj : ar[j] * rinv;
                     ar[j] = lij;
 #pragma unroll
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT) band_blocked_kernel(BandSo
 template <int KB, int Q>
 static void launch_blocked_t(const BandSolveArgs& a, cudaStream_t st) {
     using G = BlkGeom<KB, Q>;
-    size_t smem = ((size_t)G::WREG + (size_t)(Q + 1) * KB + 2 * KB + 2 * (Q + 1) * KB + (size_t)a.T * (Q + 1) + a.RD + 48) *
+    size_t smem = ((size_t)G::WREG + (size_t)(Q + 1) * KB + 2 * KB + 2 * (Q + 1) * KB + (size_t)a.T * (Q + 1) + a.RD + 48 + (KB * (KB + 1) / 2 + 3) / 4) *
                   sizeof(double);
     auto kern = band_blocked_kernel<KB, Q>;
     static size_t max_set = 0;
