@@ -37,6 +37,11 @@ WORKLOADS = {
                label='Gaussian BTF 4096x1024x64x3 reps, nembeds=16, tf_order=2, 20% NaN'),
     'c1': dict(N=11, M=12, T=20, R=1, K=3, order=2, nan=0.0,
                label='examples/gaussian_tensor_filtering.py shape 11x12x20x1, nembeds=3, tf_order=2'),
+    # BASELINE.json configs[4]; rows scale with the GPU count (8192 per GPU): at --gpus 8 this IS the
+    # 65536 x 8192 x 128 x 2 configuration, smaller counts run its weak-scaled slice.  The shard is
+    # generated on the device piecewise (1.1 TB of raw FP64 never exists on the host).
+    'c5': dict(N=8192, M=8192, T=128, R=2, K=32, order=2, nan=0.2, device_data=True, weak=True,
+               label='Gaussian BTF 8192*G x 8192 x 128 x 2 reps, nembeds=32, tf_order=2, 20% NaN (C5 at G=8)'),
     'small': dict(N=512, M=128, T=32, R=3, K=16, order=2, nan=0.2,
                   label='Gaussian BTF 512x128x32x3 reps, nembeds=16, tf_order=2, 20% NaN (smoke size)'),
 }
@@ -78,6 +83,34 @@ def make_host_data(cfg, rows=None, pinned=True, seed=2):
         b = min(r1 - r0, a + step)
         fill_rows(Y, Wl, V, a, b, cfg, seed + 17 * r0)
     return Y, W, V
+
+
+def fill_device_shard(eng, cfg, rows, device):
+    """Generate this rank's rows on the GPU in pieces (torch is only the generator here) and
+    stream them through the pre-reduction (btf_set_data_gaussian_rows)."""
+    import torch
+    dev = torch.device('cuda', device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    N, M, T, R, K = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K']
+    V = torch.randn(M, T, K, generator=g, device=dev, dtype=torch.float64)
+    V = (V * (torch.rand(M, T, 1, generator=g, device=dev) < 0.3)).flip(1).cumsum(1).flip(1) * 0.5
+    Vf = V.reshape(M * T, K)
+    r0, r1 = rows
+    g.manual_seed(99 + r0)
+    piece = max(1, (1 << 30) // (M * T * R * 8))
+    first = True
+    for a in range(r0, r1, piece):
+        b = min(r1, a + piece)
+        W = torch.randn(b - a, K, generator=g, device=dev, dtype=torch.float64)
+        Y = (W @ Vf.T).reshape(b - a, M, T, 1) + torch.randn(b - a, M, T, R, generator=g, device=dev, dtype=torch.float64)
+        if cfg['nan'] > 0:
+            Y[torch.rand(Y.shape, generator=g, device=dev) < cfg['nan']] = float('nan')
+        torch.cuda.synchronize()
+        eng.set_data_gaussian_rows_device(Y.data_ptr(), a - r0, b - a, R, first)
+        first = False
+        del Y, W
+    torch.cuda.empty_cache()
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -188,10 +221,14 @@ def bench_ours(args):
     from functionalmf_b200.engine import Engine, fp64_peak, hbm_copy_gbs, pinned_empty
     from functionalmf_b200.distributed import Shard, agree_unique_id
 
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line
+    if cfg.get('weak'):
+        cfg['N'] = cfg['N'] * world
     if world != args.gpus:
         raise SystemExit('--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run' % (args.gpus, world))
     torch.cuda.set_device(local)
@@ -218,11 +255,7 @@ def bench_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    t_gen = time.perf_counter()
-    Y, Wt, Vt = make_host_data(cfg, rows=rows)
-    t_gen = time.perf_counter() - t_gen
-
-    # ---------------- end-to-end leg: host buffers -> run_gibbs-style segment -> host samples
+    device_data = bool(cfg.get('device_data'))
     eng = Engine(N, M, T, nembeds=K, tf_order=order, **opts)
     if world > 1:
         eng.nccl_init(agree_unique_id())
@@ -230,20 +263,36 @@ def bench_ours(args):
     eng.init_state(127)
     eng.set('sigma2', [0.5]); eng.set('lam2', [0.1]); eng.set('nu2', [1.0])
     K_e2e = args.steps
-    res_W = pinned_empty((K_e2e, N, K)); res_V = pinned_empty((K_e2e, M, T, K))
-    res_T = pinned_empty((K_e2e, M, RD)); res_S = pinned_empty((K_e2e, 4))
-    barrier()
-    l0 = eng.kernel_launches
-    t0 = time.perf_counter()
-    eng.set_data_gaussian(Y)
-    eng.run_segment(K_e2e, 0, 1, 0, W=res_W, V=res_V, Tau2=res_T, scalars=res_S)
-    eng.synchronize()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_launches = eng.kernel_launches - l0
-    assert np.all(np.isfinite(res_S)) and np.all(np.isfinite(res_V[-1]))
-    h2d = Y.nbytes / float(K_e2e)
-    d2h = (res_W[0].nbytes + res_V[0].nbytes + res_T[0].nbytes + res_S[0].nbytes)
+    e2e = None
+    e2e_launches = 0
+    t_gen = time.perf_counter()
+    if device_data:
+        fill_device_shard(eng, cfg, rows, local)
+        t_gen = time.perf_counter() - t_gen
+        e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
+               'note': 'shard generated on the device; no host copy of this workload exists'}
+    else:
+        Y, Wt, Vt = make_host_data(cfg, rows=rows)
+        t_gen = time.perf_counter() - t_gen
+        # ------------ end-to-end leg: host buffers -> run_gibbs-style segment -> host samples
+        res_W = pinned_empty((K_e2e, N, K)); res_V = pinned_empty((K_e2e, M, T, K))
+        res_T = pinned_empty((K_e2e, M, RD)); res_S = pinned_empty((K_e2e, 4))
+        barrier()
+        l0 = eng.kernel_launches
+        t0 = time.perf_counter()
+        eng.set_data_gaussian(Y)
+        t_up = time.perf_counter() - t0
+        eng.run_segment(K_e2e, 0, 1, 0, W=res_W, V=res_V, Tau2=res_T, scalars=res_S)
+        eng.synchronize()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_launches = eng.kernel_launches - l0
+        assert np.all(np.isfinite(res_S)) and np.all(np.isfinite(res_V[-1]))
+        d2h = (res_W[0].nbytes + res_V[0].nbytes + res_T[0].nbytes + res_S[0].nbytes)
+        e2e = {'value': K_e2e / e2e_s, 'unit': 'sweeps/s', 'h2d_bytes_per_step': Y.nbytes / float(K_e2e),
+               'd2h_bytes_per_step': d2h, 'seconds': e2e_s, 'upload_seconds': t_up,
+               'includes': 'H2D of Y (%.2f GB per rank, once) + pre-reduction, %d sweeps, D2H of W,V,Tau2,scalars '
+                           'every sweep' % (Y.nbytes / 1e9, K_e2e)}
 
     # ---------------- device-resident leg (data already in HBM from the e2e leg)
     for _ in range(max(3, args.warmup)):
@@ -283,15 +332,12 @@ def bench_ours(args):
             'metric': 'Gibbs sweeps/sec', 'value': args.steps / (ms * 1e-3), 'unit': 'sweeps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'scaling': 'weak' if cfg.get('weak') else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': cfg['label'], 'shape': [N, M, T, R], 'nembeds': K, 'tf_order': order,
                        'nan_frac': cfg['nan'], 'l2': 'inputs (%.2f GB compact) larger than L2' % (cells * 9 / 1e9),
                        'parallelism': 'rows+cols sharded x%d' % world if world > 1 else 'single GPU',
                        'sweep': 'nu2,sigma2,Tau2,lam2,W,V (ref_compat lam2)'},
-            'e2e': {'value': K_e2e / e2e_s, 'unit': 'sweeps/s', 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'seconds': e2e_s,
-                    'includes': 'H2D of Y (%.2f GB, once), pre-reduction, %d sweeps, D2H of W,V,Tau2,scalars every sweep'
-                                % (Y.nbytes / 1e9, K_e2e)},
+            'e2e': e2e,
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
@@ -308,7 +354,7 @@ def bench_ours(args):
             'e2e_gpu_launches': int(e2e_launches),
             'datagen_seconds': t_gen,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not device_data:
             out['cpu_baseline'] = cpu_baseline(cfg, budget_s=args.cpu_budget)
     eng.close()
     if world > 1:

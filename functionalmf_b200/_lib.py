@@ -60,6 +60,7 @@ SIGNATURES = {
     'btf_destroy': (None, [_P]),
     'btf_last_error': (C.c_char_p, []),
     'btf_set_data_gaussian': (C.c_int, [_P, _P, C.c_int32]),
+    'btf_set_data_gaussian_rows': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'btf_set_data_binomial': (C.c_int, [_P, _P, _P]),
     'btf_set_data_negbin': (C.c_int, [_P, _P, C.c_int32]),
     'btf_set_state': (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),

@@ -231,39 +231,50 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 for (int c = 0; c < KB; ++c) acc += x[c] * ycur[c];
                 bw[((t + u) % (Q + 1)) * KB + irow] -= acc;
             }
-            {   // block column t -> global (unpadded blocks), and the row-band copy for diagnostics
+            {   // block column t -> global (unpadded blocks): 16-byte copies, slots resolved per block
                 double* dstg = Lg + (size_t)t * (Q + 1) * KK;
-                for (int e = tid; e < (Q + 1) * KK; e += NT) {
-                    const int ub = e / KK, rem = e % KK, i = rem / KB, c = rem % KB;
-                    double v = 0.0;
-                    if (t + ub < T) v = Wb[G::slot(t + ub, ub) * BLK + i * KS + c];
-                    dstg[e] = v;
-                    if (a.diag_chol && t + ub < T) {
-                        const int dist = ub * KB + i - c;
-                        if (dist >= 0 && dist <= kd)
-                            a.diag_chol[((size_t)jl * n + (t + ub) * KB + i) * LS + kd - dist] = v;
+#pragma unroll
+                for (int ub = 0; ub <= Q; ++ub) {
+                    const bool live = t + ub < T;
+                    const double* srcb = Wb + G::slot(t + ub, ub) * BLK;
+                    double2* dst2 = reinterpret_cast<double2*>(dstg + ub * KK);
+                    for (int e = tid; e < KK / 2; e += NT) {
+                        const int i = e / (KB / 2), c2 = e % (KB / 2);
+                        double2 v = make_double2(0.0, 0.0);
+                        if (live) v = *reinterpret_cast<const double2*>(srcb + i * KS + 2 * c2);
+                        dst2[e] = v;
+                    }
+                    if (a.diag_chol && live) {
+                        for (int e = tid; e < KK; e += NT) {
+                            const int i = e / KB, c = e % KB, dist = ub * KB + i - c;
+                            if (dist >= 0 && dist <= kd)
+                                a.diag_chol[((size_t)jl * n + (t + ub) * KB + i) * LS + kd - dist] = srcb[i * KS + c];
+                        }
                     }
                 }
             }
-            {   // A_uv -= L_ut L_vt^T on the tensor pipe: one (pair, 8x8 tile) per warp iteration
-                constexpr int TB = KB / 8, TPB = TB * TB, NPAIR = Q * (Q + 1) / 2;
-                for (int item = warp; item < NPAIR * TPB; item += NT / 32) {
-                    const int pr = item / TPB, tl = item % TPB, tm = tl / TB, tn = tl % TB;
-                    // decode pair index -> (uu >= vv >= 1)
-                    int uu = 1, rem = pr;
-                    while (rem >= uu) { rem -= uu; ++uu; }
-                    const int vv = rem + 1;
+            {   // A_uv -= L_ut L_vt^T on the tensor pipe; pairs unrolled statically (window slots
+                // are then modulo-by-constant), the 8x8 tiles of a pair are spread over the warps
+                constexpr int TB = KB / 8, TPB = TB * TB;
+#pragma unroll
+                for (int uu = 1; uu <= Q; ++uu) {
                     if (t + uu >= T) continue;
                     const double* A = Wb + G::slot(t + uu, uu) * BLK;
-                    const double* B = Wb + G::slot(t + vv, vv) * BLK;
-                    double* C = Wb + G::slot(t + uu, uu - vv) * BLK;
-                    double* cp = C + (tm * 8 + (lane >> 2)) * KS + tn * 8 + (lane & 3) * 2;
-                    double c0 = cp[0], c1 = cp[1];
-                    const double* ap = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3);
-                    const double* bp = B + (tn * 8 + (lane >> 2)) * KS + (lane & 3);
 #pragma unroll
-                    for (int ks = 0; ks < KB / 4; ++ks) dmma884(c0, c1, -ap[ks * 4], bp[ks * 4]);
-                    cp[0] = c0; cp[1] = c1;
+                    for (int vv = 1; vv <= uu; ++vv) {
+                        const double* B = Wb + G::slot(t + vv, vv) * BLK;
+                        double* C = Wb + G::slot(t + uu, uu - vv) * BLK;
+                        for (int tl = warp; tl < TPB; tl += NT / 32) {
+                            const int tm = tl / TB, tn = tl % TB;
+                            double* cp = C + (tm * 8 + (lane >> 2)) * KS + tn * 8 + (lane & 3) * 2;
+                            double c0 = cp[0], c1 = cp[1];
+                            const double* ap = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3);
+                            const double* bp = B + (tn * 8 + (lane >> 2)) * KS + (lane & 3);
+#pragma unroll
+                            for (int ks = 0; ks < KB / 4; ++ks) dmma884(c0, c1, -ap[ks * 4], bp[ks * 4]);
+                            cp[0] = c0; cp[1] = c1;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -362,13 +373,29 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
             } else {
                 k1 = c - L;
             }
-            for (int t = 0; t < T; ++t) {
-                const double* sb = stats0 + (size_t)t * nco + c;
-                const double* v = Vout + (size_t)t * KB;
-                double sv = 0.0;
-                for (int s = 0; s < a.nsplit; ++s) sv += sb[s * a.split_stride];
-                accum += wgt * sv * v[k1] * (c < L ? v[k2] : 1.0);
+            const double* sb = stats0 + c;
+            const double* v = Vout;
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            int t = 0;
+            // four independent chains of loads per thread (the statistics come from L2 / HBM)
+            for (; t + 4 <= T; t += 4) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for (int s = 0; s < a.nsplit; ++s) {
+                    const double* sp = sb + s * a.split_stride + (size_t)t * nco;
+                    s0 += sp[0]; s1 += sp[nco]; s2 += sp[2 * nco]; s3 += sp[3 * nco];
+                }
+                const double* vt = v + (size_t)t * KB;
+                p0 += s0 * vt[k1] * (c < L ? vt[k2] : 1.0);
+                p1 += s1 * vt[KB + k1] * (c < L ? vt[KB + k2] : 1.0);
+                p2 += s2 * vt[2 * KB + k1] * (c < L ? vt[2 * KB + k2] : 1.0);
+                p3 += s3 * vt[3 * KB + k1] * (c < L ? vt[3 * KB + k2] : 1.0);
             }
+            for (; t < T; ++t) {
+                double sv = 0.0;
+                for (int s = 0; s < a.nsplit; ++s) sv += sb[s * a.split_stride + (size_t)t * nco];
+                p0 += sv * v[(size_t)t * KB + k1] * (c < L ? v[(size_t)t * KB + k2] : 1.0);
+            }
+            accum += wgt * ((p0 + p1) + (p2 + p3));
         }
         double tot = block_sum(accum, red);
         if (tid == 0) a.resid_partials[jl] = tot;

@@ -325,28 +325,32 @@ static int upload_rows(btf_engine* e, const double* src, size_t row_elems, int r
     return BTF_OK;
 }
 
-int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps) {
+// Pre-reduce `nrows` local rows starting at local row `row0` (streaming form for shards that
+// are generated or loaded piecewise; reset != 0 clears the running totals first).
+int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int32_t nrows, int32_t nreps,
+                               int32_t reset) {
     if (!e || !Y || nreps < 1 || nreps > 255) return set_err(BTF_EINVAL, "bad arguments (1 <= nreps <= 255)");
     if (e->cfg.likelihood != BTF_GAUSSIAN) return set_err(BTF_ESTATE, "engine is not Gaussian");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > e->nloc) return set_err(BTF_EINVAL, "row range outside the shard");
     CK(cudaSetDevice(e->cfg.device));
     free_graph(e);
     e->nreps = nreps;
     const size_t row_elems = (size_t)e->P * nreps;
-    CK(cudaMemsetAsync(&e->scal->ss_total, 0, 2 * sizeof(double), e->stream));   // ss_total, n_obs
+    if (reset) CK(cudaMemsetAsync(&e->scal->ss_total, 0, 2 * sizeof(double), e->stream));   // ss_total, n_obs
     const bool on_dev = is_device_ptr(Y);
     double* staging = nullptr;
-    int chunk = e->nloc;
+    int chunk = nrows;
     if (!on_dev) {
-        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->nloc, ((size_t)256 << 20) / (row_elems * 8)));
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nrows, 1), ((size_t)256 << 20) / (row_elems * 8)));
         CK(cudaMalloc((void**)&staging, (size_t)chunk * row_elems * sizeof(double)));
     }
-    for (int r0 = 0; r0 < e->nloc; r0 += chunk) {
-        int rows = std::min(chunk, e->nloc - r0);
+    for (int r0 = 0; r0 < nrows; r0 += chunk) {
+        int rows = std::min(chunk, nrows - r0);
         const double* src = on_dev ? Y + (size_t)r0 * row_elems : staging;
         if (!on_dev) { int rc = upload_rows(e, Y, row_elems, r0, rows, staging); if (rc) return rc; }
         int nb = 0;
-        launch_prereduce_gaussian(src, rows, e->P, nreps, e->cnt + (size_t)r0 * e->Ppad, e->S + (size_t)r0 * e->Ppad,
-                                  e->Ppad, e->partials, &nb, e->stream);
+        const size_t o = (size_t)(row0 + r0) * e->Ppad;
+        launch_prereduce_gaussian(src, rows, e->P, nreps, e->cnt + o, e->S + o, e->Ppad, e->partials, &nb, e->stream);
         launch_reduce_add(e->partials, nb, 2, &e->scal->ss_total, e->stream);
         launch_reduce_add(e->partials + 1, nb, 2, &e->scal->n_obs, e->stream);
         e->launches += 3;
@@ -356,6 +360,11 @@ int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps) {
     CK(cudaGetLastError());
     e->has_data = true; e->data_reduced = false; e->resid_valid = false;
     return BTF_OK;
+}
+
+int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    return btf_set_data_gaussian_rows(e, Y, 0, e->nloc, nreps, 1);
 }
 
 int btf_set_data_binomial(btf_engine* e, const double* Ys, const double* Nt) {

@@ -90,6 +90,11 @@ class Engine(object):
     def set_data_gaussian_device(self, dev_ptr, nreps):
         L.check(self.lib.btf_set_data_gaussian(self._h, C.c_void_p(int(dev_ptr)), int(nreps)))
 
+    def set_data_gaussian_rows_device(self, dev_ptr, row0, nrows, nreps, reset):
+        """Streaming form: a device-resident piece [nrows, M, T, nreps] of the local shard."""
+        L.check(self.lib.btf_set_data_gaussian_rows(self._h, C.c_void_p(int(dev_ptr)), int(row0), int(nrows),
+                                                    int(nreps), 1 if reset else 0))
+
     def set_data_binomial(self, Y, Nt):
         Y, Nt = _f64(Y), _f64(Nt)
         if Y.shape != (self.nloc, self.M, self.T) or Nt.shape != Y.shape:

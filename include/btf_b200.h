@@ -78,6 +78,9 @@ const char* btf_last_error(void);
  * [row_end-row_begin, M, T, nreps]; NaN = missing.  Host or device pointers are
  * both accepted (detected with cudaPointerGetAttributes). */
 int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps);
+/* streaming form: rows [row0, row0+nrows) of the local shard; reset != 0 on the first piece */
+int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int32_t nrows, int32_t nreps,
+                               int32_t reset);
 int btf_set_data_binomial(btf_engine* e, const double* Ysucc, const double* Ntrials);
 int btf_set_data_negbin(btf_engine* e, const double* Y, int32_t nreps);
 
