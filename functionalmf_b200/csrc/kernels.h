@@ -23,6 +23,7 @@ struct StatsPlan {
     int K, L, nct_z, nct_f, zw;
     int BM, KC;
     int mtiles, nchunks, nsplit, chunks_per_split;
+    int overlap;      // 1: Z generation overlapped with the DMMA loop (compile-time-K kernels)
     size_t smem_bytes;
     size_t out_elems_per_split;   // m_valid * (L+K)
 };

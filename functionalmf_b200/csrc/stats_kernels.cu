@@ -18,6 +18,7 @@
 #include "kernels.h"
 #include <stdio.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace btf {
 
@@ -343,6 +344,220 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
     }
 }
 
+// Overlapped variant (compile-time K only): the Z tile of chunk c+1 is generated INSIDE the
+// DMMA loop of chunk c (four rows per k-step, spread over the 8 warps), from a factor tile
+// that is prefetched two chunks ahead; Z is double buffered.  The tensor pipe no longer idles
+// during Z generation and one barrier per chunk replaces three.
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
+__global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a) {
+    static_assert(WR * WC == 8, "Z generation inside the DMMA loop is laid out for 8 warps");
+    constexpr int NT = 32 * WR * WC;
+    constexpr int RT = BM / 8 / WR;
+    using G = TileGeom<TRANS, WT, BM, KC>;
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    constexpr int K = KFIX, L = K * (K + 1) / 2;
+    constexpr int nct_z = cdiv(L, 8), nct_f = cdiv(K, 8);
+    constexpr int ZPW = cdiv(nct_z, WC), FPW = cdiv(nct_f, WC);
+    constexpr int ncw = (nct_z + nct_f) * 8;
+    constexpr int CZ = cdiv(ncw, 32), CZH = (CZ + 1) / 2;
+    constexpr int fbytes = ((KC * K * 8) + 15) & ~15;
+    constexpr int dbytes = G::WBYTES + G::SBYTES;
+    const int zw = a.zw;
+    unsigned char* data0 = smem;                                   // [2][dbytes]
+    unsigned char* f0 = smem + 2 * dbytes;                         // [3][fbytes]
+    double* z0 = reinterpret_cast<double*>(smem + 2 * dbytes + 3 * fbytes);   // [2][KC][zw]
+    const int zstride = KC * zw;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp / WC, wc = warp % WC;
+    const int m0 = blockIdx.x * BM;
+    const int split = blockIdx.y;
+    const int c_begin = split * a.chunks_per_split;
+    const int c_end = min(a.nchunks, c_begin + a.chunks_per_split);
+
+    int zcode[CZ];
+#pragma unroll
+    for (int q = 0; q < CZ; ++q) {
+        int c = lane + 32 * q;
+        int code = 0;
+        if (c < ncw) {
+            if (c < nct_z * 8) {
+                if (c < L) {
+                    int k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
+                    while (k1 * (k1 + 1) / 2 > c) --k1;
+                    while ((k1 + 1) * (k1 + 2) / 2 <= c) ++k1;
+                    int k2 = c - k1 * (k1 + 1) / 2;
+                    code = (1 << 30) | (k1 << 8) | k2;
+                }
+            } else {
+                int cf = c - nct_z * 8;
+                if (cf < K) code = (2 << 30) | (cf << 8);
+            }
+        }
+        zcode[q] = code;
+    }
+
+    double acc[RT][CTM][2];
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int c = 0; c < CTM; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    auto load_data = [&](int stage, int chunk) {
+        unsigned char* base = data0 + stage * dbytes;
+        WT* wtile = reinterpret_cast<WT*>(base);
+        double* stile = reinterpret_cast<double*>(base + G::WBYTES);
+        const int k0 = chunk * KC;
+        const WT* wsrc = reinterpret_cast<const WT*>(a.wt);
+        if (!TRANS) {
+            constexpr int WP = KC * (int)sizeof(WT) / 16;
+            for (int e = tid; e < BM * WP; e += NT) {
+                int r = e / WP, q = e % WP;
+                cp_async16(reinterpret_cast<unsigned char*>(wtile + r * G::WSTR) + 16 * q,
+                           reinterpret_cast<const unsigned char*>(wsrc + (long long)(m0 + r) * a.ld + k0) + 16 * q);
+            }
+            constexpr int SP = KC / 2;
+            for (int e = tid; e < BM * SP; e += NT) {
+                int r = e / SP, q = e % SP;
+                cp_async16(stile + r * G::SSTR + 2 * q, a.sv + (long long)(m0 + r) * a.ld + k0 + 2 * q);
+            }
+        } else {
+            constexpr int WP = BM * (int)sizeof(WT) / 16;
+            for (int e = tid; e < KC * WP; e += NT) {
+                int r = e / WP, q = e % WP;
+                cp_async16(reinterpret_cast<unsigned char*>(wtile + r * G::WSTR) + 16 * q,
+                           reinterpret_cast<const unsigned char*>(wsrc + (long long)(k0 + r) * a.ld + m0) + 16 * q);
+            }
+            constexpr int SP = BM / 2;
+            for (int e = tid; e < KC * SP; e += NT) {
+                int r = e / SP, q = e % SP;
+                cp_async16(stile + r * G::SSTR + 2 * q, a.sv + (long long)(k0 + r) * a.ld + m0 + 2 * q);
+            }
+        }
+    };
+    auto load_f = [&](int fstage, int chunk) {
+        double* ftile = reinterpret_cast<double*>(f0 + fstage * fbytes);
+        const double* fsrc = a.F + (long long)chunk * KC * K;
+        for (int e = tid; e < (KC * K) / 2; e += NT) cp_async16(ftile + 2 * e, fsrc + 2 * e);
+    };
+    // one row of Z for the columns zcode[qlo..qhi) of this lane
+    auto gen_row = [&](double* zdst, const double* fr, int qlo, int qhi) {
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) {
+            if (q >= qlo && q < qhi) {
+                const int cc = lane + 32 * q;
+                if (cc < ncw) {
+                    const int code = zcode[q];
+                    const int ty = (unsigned)code >> 30;
+                    double v = 0.0;
+                    if (ty == 1) v = fr[(code >> 8) & 0xff] * fr[code & 0xff];
+                    else if (ty == 2) v = fr[(code >> 8) & 0xff];
+                    zdst[cc] = v;
+                }
+            }
+        }
+    };
+
+    const int zoff_z = wc * ZPW * 8 + (lane >> 2);
+    const int zoff_f = (nct_z + wc * FPW) * 8 + (lane >> 2);
+
+    if (c_begin < c_end) {
+        load_data(0, c_begin);
+        load_f(0, c_begin);
+        if (c_begin + 1 < c_end) load_f(1, c_begin + 1);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (c_begin < c_end) {
+        const double* ftile = reinterpret_cast<const double*>(f0);
+        for (int k = warp; k < KC; k += NT / 32) gen_row(z0 + k * zw, ftile + k * K, 0, CZ);
+    }
+    __syncthreads();
+
+    const int grow = warp & 3;                    // row (within a k-step) this warp generates
+    const int gqlo = (warp >> 2) ? CZH : 0, gqhi = (warp >> 2) ? CZ : CZH;
+
+    for (int c = c_begin; c < c_end; ++c) {
+        const int it = c - c_begin;
+        const bool more = c + 1 < c_end;
+        if (more) load_data((it + 1) & 1, c + 1);
+        if (c + 2 < c_end) load_f((it + 2) % 3, c + 2);
+        cp_async_commit();
+
+        unsigned char* base = data0 + (it & 1) * dbytes;
+        const WT* wtile = reinterpret_cast<const WT*>(base);
+        const double* stile = reinterpret_cast<const double*>(base + G::WBYTES);
+        const double* zcur = z0 + (it & 1) * zstride;
+        double* znext = z0 + ((it + 1) & 1) * zstride;
+        const double* fnext = reinterpret_cast<const double*>(f0 + ((it + 1) % 3) * fbytes);
+
+#pragma unroll 2
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            const int kl = kk * 4 + (lane & 3);
+            double aw[RT], as[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int ml = (wr * RT + r) * 8 + (lane >> 2);
+                if (!TRANS) {
+                    aw[r] = (double)wtile[ml * G::WSTR + kl];
+                    as[r] = stile[ml * G::SSTR + kl];
+                } else {
+                    aw[r] = (double)wtile[kl * G::WSTR + ml];
+                    as[r] = stile[kl * G::SSTR + ml];
+                }
+            }
+            const double* zrow = zcur + kl * zw;
+#pragma unroll
+            for (int ci = 0; ci < CTM; ++ci) {
+                const bool isz = ci < ZPW;
+                const double b = isz ? zrow[zoff_z + ci * 8] : zrow[zoff_f + (ci - ZPW) * 8];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+            }
+            // four rows of the NEXT chunk's Z tile, issued in the shadow of the DMMAs above
+            if (more) {
+                const int gk = kk * 4 + grow;
+                gen_row(znext + gk * zw, fnext + gk * K, gqlo, gqhi);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    double* out = a.out + (long long)split * a.out_split_stride;
+    constexpr int nco = L + K;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int m = m0 + (wr * RT + r) * 8 + (lane >> 2);
+        if (m < a.m_valid) {
+#pragma unroll
+            for (int ci = 0; ci < CTM; ++ci) {
+                const bool isz = ci < ZPW;
+                const int tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
+                if (ci < ZPW + FPW && tl < (isz ? nct_z : nct_f)) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = tl * 8 + (lane & 3) * 2 + h;
+                        int oc = -1;
+                        if (isz) { if (cc < L) oc = cc; }
+                        else if (cc < K) oc = L + cc;
+                        if (oc >= 0) out[(long long)m * nco + oc] = acc[r][ci][h];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
+static size_t stats_smem_ovl(int K, int zw) {
+    using G = TileGeom<TRANS, WT, BM, KC>;
+    size_t fbytes = ((size_t)(KC * K * 8) + 15) & ~(size_t)15;
+    return 2 * (size_t)(G::WBYTES + G::SBYTES) + 3 * fbytes + 2 * (size_t)KC * zw * 8;
+}
+
 template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT>
 static size_t stats_smem(int K, int zw) {
     using G = TileGeom<TRANS, WT, BM, KC>;
@@ -359,6 +574,24 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
     auto kern = stats_kernel<BM, WR, WC, CTM, KC, TRANS, WT, KFIX>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    dim3 grid(p.mtiles, p.nsplit);
+    kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
+}
+
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
+static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double* sv, const double* F,
+                               long long ld, int m_valid, double* out, cudaStream_t st) {
+    StatsKArgs a;
+    a.wt = wt; a.sv = sv; a.F = F; a.out = out; a.ld = ld;
+    a.K = p.K; a.L = p.L; a.nct_z = p.nct_z; a.nct_f = p.nct_f; a.zw = p.zw;
+    a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
+    a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
+    auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -440,6 +673,19 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
         default: p->smem_bytes = SMEM_OF(BTF_CFG5); break;
     }
 #undef SMEM_OF
+    // compile-time-K configurations: overlap Z generation with the DMMAs when the double
+    // buffers fit (BTF_STATS_NO_OVERLAP=1 keeps the three-phase kernel for A/B measurements)
+    p->overlap = 0;
+    static const bool no_ovl = getenv("BTF_STATS_NO_OVERLAP") != nullptr;
+    if (p->cfg >= 3 && !no_ovl) {
+#define SMEM_OVL(...) (trans ? (weights_f64 ? stats_smem_ovl<__VA_ARGS__, true, double>(K, p->zw)   \
+                                            : stats_smem_ovl<__VA_ARGS__, true, uint8_t>(K, p->zw)) \
+                             : (weights_f64 ? stats_smem_ovl<__VA_ARGS__, false, double>(K, p->zw)  \
+                                            : stats_smem_ovl<__VA_ARGS__, false, uint8_t>(K, p->zw)))
+        size_t so = p->cfg == 3 ? SMEM_OVL(BTF_CFG3) : (p->cfg == 4 ? SMEM_OVL(BTF_CFG4) : SMEM_OVL(BTF_CFG5));
+#undef SMEM_OVL
+        if (so <= 220 * 1024) { p->overlap = 1; p->smem_bytes = so; }
+    }
     return p->smem_bytes <= 220 * 1024;
 }
 
@@ -455,6 +701,24 @@ void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* 
             else launch_stats_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
         }                                                                                                        \
     } while (0)
+#define DISPATCH_OVL(KF, ...)                                                                                        \
+    do {                                                                                                             \
+        if (trans) {                                                                                                 \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, true, double, KF>(p, wt, sv, F, ld, m_valid, out, st);  \
+            else launch_stats_ovl_t<__VA_ARGS__, true, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);             \
+        } else {                                                                                                     \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, false, double, KF>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_ovl_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
+        }                                                                                                            \
+    } while (0)
+    if (p.overlap) {
+        switch (p.cfg) {
+            case 3: DISPATCH_OVL(16, BTF_CFG3); return;
+            case 4: DISPATCH_OVL(32, BTF_CFG4); return;
+            default: DISPATCH_OVL(8, BTF_CFG5); return;
+        }
+    }
+#undef DISPATCH_OVL
     switch (p.cfg) {
         case 0: DISPATCH(0, BTF_CFG0); break;
         case 1: DISPATCH(0, BTF_CFG1); break;
