@@ -42,43 +42,62 @@ __device__ __forceinline__ double pg_acoef(int n, double x) {
     return exp(-1.5 * (log(0.5 * PG_PI) + log(x)) + log(k) - 2.0 * (n + 0.5) * (n + 0.5) / x);
 }
 
-__device__ double pg_rtigauss(Rng& rng, double Z) {
+// Truncated inverse-Gaussian(1/Z, 1) on (0, t].  `u0` is a spare uniform the caller already
+// holds (used for the first acceptance test, so the common path costs one Philox call).
+__device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
     const double t = PG_TRUNC;
-    if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0)
+    bool have_u0 = true;
+    if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0): exponential-tail proposal
         for (int it = 0; it < 10000; ++it) {
-            double e1, e2;
+            double e1 = 0.0, e2 = 0.0;
             for (int k = 0; k < 10000; ++k) {
                 double2 u = rng.uniform2();
                 e1 = -log(u.x); e2 = -log(u.y);
                 if (e1 * e1 <= 2.0 * e2 / t) break;
             }
-            double X = t / ((1.0 + t * e1) * (1.0 + t * e1));
-            if (rng.uniform() <= exp(-0.5 * Z * Z * X)) return X;
+            const double X = t / ((1.0 + t * e1) * (1.0 + t * e1));
+            const double ua = have_u0 ? u0 : rng.uniform();
+            have_u0 = false;
+            if (ua <= exp(-0.5 * Z * Z * X)) return X;
         }
         return t;
     }
     const double mu = 1.0 / Z;
     for (int it = 0; it < 10000; ++it) {
-        double nn = rng.normal();
-        double Y = nn * nn;
+        double2 nu = rng.normal2();
+        double ua = have_u0 ? u0 : rng.uniform();
+        have_u0 = false;
+        double Y = nu.x * nu.x;
         double X = mu + 0.5 * mu * mu * Y - 0.5 * mu * sqrt(4.0 * mu * Y + (mu * Y) * (mu * Y));
-        if (rng.uniform() > mu / (mu + X)) X = mu * mu / X;
+        if (ua > mu / (mu + X)) X = mu * mu / X;
         if (X <= t) return X;
     }
     return t;
 }
 
+// One PG(1, z) draw (Devroye / Polson-Scott-Windle alternating series).  The first
+// acceptance test  U a_0 <= a_0 - a_1  only needs the ratio a_1 / a_0 = 3 exp(-4/x) (x <= t)
+// or 3 exp(-pi^2 x) (x > t): one exponential; the full coefficients are evaluated only on the
+// rare (< 0.6 %) continuation of the series.
 __device__ double pg_one(Rng& rng, const PgTilt& c) {
     for (int it = 0; it < 10000; ++it) {
+        const uint4 r = rng.next4();
+        const double u1 = Rng::to_unit(r.x, r.y), u2 = Rng::to_unit(r.z, r.w);
         double X;
-        if (rng.uniform() < c.pmass) X = PG_TRUNC + rng.exponential() / c.fz;
-        else X = pg_rtigauss(rng, c.Z);
+        if (u1 < c.pmass) X = PG_TRUNC - log(u1 / c.pmass) / c.fz;       // u1 / pmass is U(0,1) given the branch
+        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) / (1.0 - c.pmass));
+        const double ratio = 3.0 * (X > PG_TRUNC ? exp(-PG_PI * PG_PI * X) : exp(-4.0 / X));
+        if (u2 <= 1.0 - ratio) return 0.25 * X;
+        // continue the series from n = 2 with explicit coefficients
         double S = pg_acoef(0, X);
-        const double Y = rng.uniform() * S;
-        for (int n = 1; n < 400; ++n) {
+        const double Y = u2 * S;
+        S -= pg_acoef(1, X);
+        bool rejected = false;
+        for (int n = 2; n < 400; ++n) {
             if (n & 1) { S -= pg_acoef(n, X); if (Y <= S) return 0.25 * X; }
-            else { S += pg_acoef(n, X); if (Y > S) break; }
+            else { S += pg_acoef(n, X); if (Y > S) { rejected = true; break; } }
         }
+        (void)rejected;
     }
     return 0.25 * PG_TRUNC;
 }

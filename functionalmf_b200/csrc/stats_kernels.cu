@@ -677,7 +677,8 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
     // buffers fit (BTF_STATS_NO_OVERLAP=1 keeps the three-phase kernel for A/B measurements)
     p->overlap = 0;
     static const bool no_ovl = getenv("BTF_STATS_NO_OVERLAP") != nullptr;
-    if (p->cfg >= 3 && !no_ovl) {
+    // (measured on B200: +6 % at K = 16, neutral at K = 32, slower at K = 8 where Z is tiny)
+    if ((p->cfg == 3 || p->cfg == 4) && !no_ovl) {
 #define SMEM_OVL(...) (trans ? (weights_f64 ? stats_smem_ovl<__VA_ARGS__, true, double>(K, p->zw)   \
                                             : stats_smem_ovl<__VA_ARGS__, true, uint8_t>(K, p->zw)) \
                              : (weights_f64 ? stats_smem_ovl<__VA_ARGS__, false, double>(K, p->zw)  \
