@@ -29,13 +29,14 @@ for r in data:
     print('   stalls/issue:', ', '.join('%s=%.2f' % (h.split('stalled_')[1].split('_per_issue')[0], float(v)) for h, v in st))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-kernel = None
-cur = None
+acc = {}
+kernel, cur = None, None
 for r in rows:
     if r and r[0] == 'Kernel Name':
-        kernel = r[1]; cur = None; continue
+        kernel, cur = r[1], None
+        continue
     if r and r[0] == 'Address':
-        cur = {h: i for i, h in enumerate(r)}; ops = Counter(); tot = 0; lines = []
+        cur = {h: i for i, h in enumerate(r)}
         continue
     if cur is None or not r:
         continue
@@ -46,19 +47,15 @@ for r in rows:
     srcl = r[cur['Source']].strip()
     toks = srcl.split()
     op = toks[1] if toks and toks[0].startswith('@') and len(toks) > 1 else (toks[0] if toks else '?')
-    lines.append((n, srcl, kernel))
-    # flush at end handled below
-    r.append(kernel)
-    if 'acc' not in globals():
-        acc = {}
-    acc.setdefault(kernel, []).append((n, op.split('.')[0], srcl, {h: r[i] for h, i in cur.items() if h.startswith('stall_') and 'Not' not in h}))
-for kernel, items in globals().get('acc', {}).items():
+    stl = {h: r[i] for h, i in cur.items() if h.startswith('stall_') and 'Not' not in h}
+    acc.setdefault(kernel, []).append((n, op.split('.')[0], srcl, stl))
+for kernel, items in acc.items():
     tot = sum(n for n, _, _, _ in items) or 1
     print('== samples by opcode:', kernel[:100], 'total', int(tot))
     c = Counter()
     for n, op, _, _ in items:
         c[op] += n
     print('   ' + ', '.join('%s %.1f%%' % (op, 100 * n / tot) for op, n in c.most_common(12)))
-    for n, op, s, stl in sorted(items, key=lambda x: -x[0])[:14]:
+    for n, op, s, stl in sorted(items, key=lambda x: -x[0])[:12]:
         top = sorted(((k, float(v or 0)) for k, v in stl.items()), key=lambda kv: -kv[1])[:2]
         print('   %5.2f%%  %-60s %s' % (100 * n / tot, s[:60], top))
