@@ -16,6 +16,8 @@
 //         the trend-filtering band Delta^T diag(1/(lam2 tau2)) Delta
 //   backward substitution by block columns (mean and draw together), factor blocks streamed
 //   back through a cp.async double buffer.
+// Any K <= KB runs on the KB-wide instantiation: the KB - K extra unknowns per depth are
+// decoupled unit-variance dummies (identity in the diagonal blocks, zero elsewhere).
 // The live window is the lower triangle of a (Q+1) x (Q+1) block grid; diagonal d of that
 // grid is a circular buffer of Q+1-d blocks (slot = base_d + row mod (Q+1-d)), so the window
 // advances without copying: the entering row overwrites exactly the retired column blocks.
@@ -61,9 +63,11 @@ template <int KB, int Q>
 __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band_blocked_kernel(BandSolveArgs a) {
     using G = BlkGeom<KB, Q>;
     constexpr int KS = G::KS, BLK = G::BLK, NT = G::NT, KK = G::KK;
-    constexpr int L = KB * (KB + 1) / 2, nco = L + KB, kd = Q * KB, LS = kd + 1;
     extern __shared__ __align__(16) double sm[];
-    const int T = a.T, n = T * KB;
+    const int Kr = a.K;                                  // true embedding size (<= KB)
+    const int L = Kr * (Kr + 1) / 2, nco = L + Kr, kd = Q * Kr, LS = kd + 1;
+    const int T = a.T, n = T * Kr;                       // true system size (outputs, noise indices)
+    const int ni = T * KB;                               // padded system size (internal workspaces)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int jl = blockIdx.x, jg = a.col_begin + jl;
     const unsigned full = 0xffffffffu;
@@ -83,8 +87,8 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
     const double lam2 = a.scal->lam2;
     for (int r = tid; r < a.RD; r += NT) linv[r] = 1.0 / (lam2 * a.Tau2[(size_t)jg * a.RD + r]);
     if (tid == 0) fail_flag = 0;
-    for (int e = tid; e < KB * KB; e += NT) {
-        const int i = e / KB, c = e % KB;
+    for (int e = tid; e < Kr * Kr; e += NT) {
+        const int i = e / Kr, c = e % Kr;
         if (c <= i) pairtab[tri(i, c)] = (unsigned short)((i << 8) | c);
     }
     __syncthreads();
@@ -96,8 +100,8 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
     __syncthreads();
 
     // global workspace of this column: block columns [T][Q+1][KB][KB], then y [n], 1/diag [n]
-    double* Lg = a.work_L + (size_t)jl * n * (kd + KB + 1);
-    double* yg = a.work_y + (size_t)jl * 2 * n;
+    double* Lg = a.work_L + (size_t)jl * a.work_L_stride;
+    double* yg = a.work_y + (size_t)jl * a.work_y_stride;     // [y (ni) | 1 / diag(L) (ni)]
     const bool have_stats = a.stats != nullptr;
     const double* stats0 = have_stats ? a.stats + (size_t)jg * T * nco : nullptr;
 
@@ -122,12 +126,17 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 v = sv * scale;
             }
             if (c == i) v += pd;
-            if (a.diag_band) a.diag_band[((size_t)jl * n + arow * KB + i) * LS + kd - (i - c)] = v;
+            if (a.diag_band) a.diag_band[((size_t)jl * n + arow * Kr + i) * LS + kd - (i - c)] = v;
             D[i * KS + c] = v;
+        }
+        // padding rows Kr..KB-1: identity
+        for (int e = t0; e < (KB - Kr) * KB; e += nthreads) {
+            const int i = Kr + e / KB, c = e % KB;
+            if (c <= i) D[i * KS + c] = (c == i) ? 1.0 : 0.0;
         }
         for (int e = t0; e < KB; e += nthreads) {
             double sv = 0.0;
-            if (have_stats) {
+            if (have_stats && e < Kr) {
                 sv = sb[L + e];
                 for (int s = 1; s < a.nsplit; ++s) sv += sb[s * a.split_stride + L + e];
             }
@@ -141,11 +150,11 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 const double pv = Pband[(arow - d) * (Q + 1) + d];
                 for (int e = t0; e < KB * KB; e += nthreads) {
                     const int i = e / KB, c = e % KB;
-                    B[i * KS + c] = (i == c) ? pv : 0.0;
+                    B[i * KS + c] = (i == c && i < Kr) ? pv : 0.0;
                 }
                 if (a.diag_band)
-                    for (int e = t0; e < KB; e += nthreads)
-                        if (d * KB <= kd) a.diag_band[((size_t)jl * n + arow * KB + e) * LS + kd - d * KB] = pv;
+                    for (int e = t0; e < Kr; e += nthreads)
+                        a.diag_band[((size_t)jl * n + arow * Kr + e) * LS + kd - d * Kr] = pv;
             }
         }
     };
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                             if (lane >= k) ar[k] -= lij * lkj;
                         }
                     }
-                    if (lane == j) { dinv[j] = rinv; yg[n + t * KB + j] = rinv; }
+                    if (lane == j) { dinv[j] = rinv; yg[ni + t * KB + j] = rinv; }
                 }
                 if (!ok && lane == 0) fail_flag = 1;
                 if (lane < KB) {
@@ -246,9 +255,9 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                     }
                     if (a.diag_chol && live) {
                         for (int e = tid; e < KK; e += NT) {
-                            const int i = e / KB, c = e % KB, dist = ub * KB + i - c;
-                            if (dist >= 0 && dist <= kd)
-                                a.diag_chol[((size_t)jl * n + (t + ub) * KB + i) * LS + kd - dist] = srcb[i * KS + c];
+                            const int i = e / KB, c = e % KB, dist = ub * Kr + i - c;
+                            if (i < Kr && c < Kr && dist >= 0 && dist <= kd)
+                                a.diag_chol[((size_t)jl * n + (t + ub) * Kr + i) * LS + kd - dist] = srcb[i * KS + c];
                         }
                     }
                 }
@@ -323,10 +332,10 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
         if (warp < 2 && lane < KB) {
             const int rhs = warp, k = lane;
             double r = yg[t * KB + k];
-            if (rhs) {
+            if (rhs && k < Kr) {
                 double z;
-                if (a.z_inject) z = a.z_inject[(size_t)jg * n + t * KB + k];
-                else { Rng rng(a.seed, STREAM_V, sweep, (uint64_t)jg * n + t * KB + k); z = rng.normal(); }
+                if (a.z_inject) z = a.z_inject[(size_t)jg * n + t * Kr + k];
+                else { Rng rng(a.seed, STREAM_V, sweep, (uint64_t)jg * n + t * Kr + k); z = rng.normal(); }
                 r += z;
             }
 #pragma unroll
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
             }
             // triangular solve with L_tt^T inside the warp
             double xk = 0.0;
-            const double dk = yg[n + t * KB + k];
+            const double dk = yg[ni + t * KB + k];
 #pragma unroll
             for (int j = KB - 1; j >= 0; --j) {
                 const double xj = __shfl_sync(0xffffffffu >> (32 - KB), r * dk, j);
@@ -350,8 +359,10 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 if (k < j) r -= Lt[j * KB + k] * xj;
             }
             xw[(rhs * (Q + 1) + t % (Q + 1)) * KB + k] = xk;
-            if (rhs) Vout[t * KB + k] = xk;
-            else if (a.diag_mean) a.diag_mean[(size_t)jg * n + t * KB + k] = xk;
+            if (k < Kr) {
+                if (rhs) Vout[t * Kr + k] = xk;
+                else if (a.diag_mean) a.diag_mean[(size_t)jg * n + t * Kr + k] = xk;
+            }
         }
         __syncthreads();
     }
@@ -384,16 +395,16 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                     const double* sp = sb + s * a.split_stride + (size_t)t * nco;
                     s0 += sp[0]; s1 += sp[nco]; s2 += sp[2 * nco]; s3 += sp[3 * nco];
                 }
-                const double* vt = v + (size_t)t * KB;
+                const double* vt = v + (size_t)t * Kr;
                 p0 += s0 * vt[k1] * (c < L ? vt[k2] : 1.0);
-                p1 += s1 * vt[KB + k1] * (c < L ? vt[KB + k2] : 1.0);
-                p2 += s2 * vt[2 * KB + k1] * (c < L ? vt[2 * KB + k2] : 1.0);
-                p3 += s3 * vt[3 * KB + k1] * (c < L ? vt[3 * KB + k2] : 1.0);
+                p1 += s1 * vt[Kr + k1] * (c < L ? vt[Kr + k2] : 1.0);
+                p2 += s2 * vt[2 * Kr + k1] * (c < L ? vt[2 * Kr + k2] : 1.0);
+                p3 += s3 * vt[3 * Kr + k1] * (c < L ? vt[3 * Kr + k2] : 1.0);
             }
             for (; t < T; ++t) {
                 double sv = 0.0;
                 for (int s = 0; s < a.nsplit; ++s) sv += sb[s * a.split_stride + (size_t)t * nco];
-                p0 += sv * v[(size_t)t * KB + k1] * (c < L ? v[(size_t)t * KB + k2] : 1.0);
+                p0 += sv * v[(size_t)t * Kr + k1] * (c < L ? v[(size_t)t * Kr + k2] : 1.0);
             }
             accum += wgt * ((p0 + p1) + (p2 + p3));
         }
@@ -428,9 +439,9 @@ bool launch_band_solve_blocked(const BandSolveArgs& a, cudaStream_t st) {
             default: return false;                                    \
         }                                                             \
     } while (0)
-    if (a.K == 8) BTF_BLK(8);
-    if (a.K == 16) BTF_BLK(16);
-    if (a.K == 32) BTF_BLK(32);
+    if (a.K <= 8) BTF_BLK(8);
+    if (a.K <= 16) BTF_BLK(16);
+    if (a.K <= 32) BTF_BLK(32);
 #undef BTF_BLK
     return false;
 }

@@ -41,6 +41,8 @@ struct btf_engine {
     btf_config cfg;
     int N, M, T, K, order, q, kd, RD, L, nco, P, Ppad, nloc, nloc_pad, n;
     int Mloc;
+    int Kp;                      // K rounded up to the band solver's block size (8, 16, 32)
+    size_t wL_stride, wy_stride; // per-column workspace strides of the band solver
     int sm_count;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // state
@@ -260,9 +262,12 @@ int btf_create(const btf_config* c, btf_engine** out) {
     CK(dev_alloc(&e->row_stats, e->plan_row.nsplit * e->plan_row.out_elems_per_split));
     CK(dev_alloc(&e->col_stats, e->plan_col.nsplit * e->plan_col.out_elems_per_split));
 
-    // workspaces
-    CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->n * (e->kd + e->K + 1)));
-    CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->n * 2));
+    // workspaces (the blocked band solver works on K padded to 8 / 16 / 32)
+    e->Kp = e->K <= 8 ? 8 : (e->K <= 16 ? 16 : 32);
+    e->wL_stride = std::max((size_t)e->T * (e->q + 1) * e->Kp * e->Kp, (size_t)e->n * (e->kd + 1));
+    e->wy_stride = (size_t)2 * e->T * e->Kp;
+    CK(dev_alloc(&e->work_L, (size_t)std::max(e->Mloc, 1) * e->wL_stride));
+    CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->wy_stride));
     e->partials_n = std::max<size_t>((size_t)(e->Ppad / 256) * (e->nloc_pad / 64), (size_t)2 * 148 * 16) + 64;
     CK(dev_alloc(&e->partials, e->partials_n));
     CK(dev_alloc(&e->lam_partials, e->M));
@@ -726,6 +731,7 @@ static int enqueue_sweep(btf_engine* e) {
             ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
             ba.V = e->V; ba.z_inject = inj(e, "z_V"); ba.seed = c.seed;
             ba.work_L = e->work_L; ba.work_y = e->work_y;
+            ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
             ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
             const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
             ba.diag_band = diag_get(e, "V_band", bn);
@@ -954,10 +960,11 @@ int btf_init_state(btf_engine* e, int32_t init_mask) {
         double *wl = nullptr, *wy = nullptr;
         const bool tmp = e->Mloc < e->M;   // sharded engines own a smaller workspace
         if (tmp) {
-            CK(cudaMalloc((void**)&wl, (size_t)e->M * e->n * (e->kd + e->K + 1) * sizeof(double)));
-            CK(cudaMalloc((void**)&wy, (size_t)e->M * e->n * 2 * sizeof(double)));
+            CK(cudaMalloc((void**)&wl, (size_t)e->M * e->wL_stride * sizeof(double)));
+            CK(cudaMalloc((void**)&wy, (size_t)e->M * e->wy_stride * sizeof(double)));
         }
         ba.work_L = tmp ? wl : e->work_L; ba.work_y = tmp ? wy : e->work_y;
+        ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
         ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
         launch_band_solve(ba, st);
         launch_clip(e->V, (size_t)e->P * e->K, -10.0, 10.0, st);

@@ -67,7 +67,8 @@ struct BandSolveArgs {
     const double* z_inject;   // [M][T][K] or nullptr
     uint64_t seed;
     double* work_L;        // [ncols_loc][n][kd+K+1]  (scalar kernel uses the first n*(kd+1) of each)
-    double* work_y;        // [ncols_loc][2n]  y | 1/diag(L)
+    double* work_y;        // [ncols_loc][work_y_stride]  y | 1/diag(L)
+    size_t work_L_stride, work_y_stride;   // per-column strides (sized for the padded block size)
     int force_psd, attempts; double eps;
     double *diag_band, *diag_chol, *diag_mean; int* diag_retries;
     double* resid_partials;   // [ncols_loc]: sum_t v^T A v - 2 v.b   (nu2 by-product)

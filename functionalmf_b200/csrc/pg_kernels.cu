@@ -30,8 +30,16 @@ __device__ __forceinline__ PgTilt pg_setup(double z) {
     c.fz = PG_PI * PG_PI / 8.0 + 0.5 * c.Z * c.Z;
     const double rt = 1.25;   // sqrt(1 / 0.64)
     double b = rt * (PG_TRUNC * c.Z - 1.0), a = -rt * (PG_TRUNC * c.Z + 1.0);
-    double x0 = log(c.fz) + c.fz * PG_TRUNC;
-    double qdivp = 4.0 / PG_PI * (exp(x0 - c.Z + log_phi(b)) + exp(x0 + c.Z + log_phi(a)));
+    double qdivp;
+    if (c.Z < 12.0) {
+        // fz exp(fz t) [exp(-Z) Phi(b) + exp(Z) Phi(a)] without logarithms (no overflow for |z| < 24)
+        const double ez = exp(-c.Z);
+        const double pb = 0.5 * erfc(-b * 0.70710678118654752440), pa = 0.5 * erfc(-a * 0.70710678118654752440);
+        qdivp = 4.0 / PG_PI * c.fz * exp(c.fz * PG_TRUNC) * (ez * pb + pa / ez);
+    } else {
+        const double x0 = log(c.fz) + c.fz * PG_TRUNC;
+        qdivp = 4.0 / PG_PI * (exp(x0 - c.Z + log_phi(b)) + exp(x0 + c.Z + log_phi(a)));
+    }
     c.pmass = 1.0 / (1.0 + qdivp);
     return c;
 }
@@ -42,6 +50,16 @@ __device__ __forceinline__ double pg_acoef(int n, double x) {
     return exp(-1.5 * (log(0.5 * PG_PI) + log(x)) + log(k) - 2.0 * (n + 0.5) * (n + 0.5) / x);
 }
 
+// Accept/reject DECISIONS  u <= exp(x)  are taken in FP32 when they are not borderline and
+// re-evaluated in FP64 otherwise, so every decision equals the FP64 one while most FP64
+// exponentials disappear; all VALUES that reach the output are computed in FP64.
+__device__ __forceinline__ bool leq_exp(double u, double x) {
+    const float ef = __expf((float)x), uf = (float)u;
+    if (uf < ef * 0.9999f - 1e-30f) return true;
+    if (uf > ef * 1.0001f + 1e-30f) return false;
+    return u <= exp(x);
+}
+
 // Truncated inverse-Gaussian(1/Z, 1) on (0, t].  `u0` is a spare uniform the caller already
 // holds (used for the first acceptance test, so the common path costs one Philox call).
 __device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
@@ -49,16 +67,17 @@ __device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
     bool have_u0 = true;
     if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0): exponential-tail proposal
         for (int it = 0; it < 10000; ++it) {
-            double e1 = 0.0, e2 = 0.0;
+            double e1 = 0.0;
             for (int k = 0; k < 10000; ++k) {
-                double2 u = rng.uniform2();
-                e1 = -log(u.x); e2 = -log(u.y);
-                if (e1 * e1 <= 2.0 * e2 / t) break;
+                const double2 u = rng.uniform2();
+                e1 = -log(u.x);
+                // E1^2 <= 2 E2 / t  with E2 = -log(u.y)   <=>   u.y <= exp(-t E1^2 / 2)
+                if (leq_exp(u.y, -0.5 * t * e1 * e1)) break;
             }
             const double X = t / ((1.0 + t * e1) * (1.0 + t * e1));
             const double ua = have_u0 ? u0 : rng.uniform();
             have_u0 = false;
-            if (ua <= exp(-0.5 * Z * Z * X)) return X;
+            if (leq_exp(ua, -0.5 * Z * Z * X)) return X;
         }
         return t;
     }
@@ -77,8 +96,8 @@ __device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
 
 // One PG(1, z) draw (Devroye / Polson-Scott-Windle alternating series).  The first
 // acceptance test  U a_0 <= a_0 - a_1  only needs the ratio a_1 / a_0 = 3 exp(-4/x) (x <= t)
-// or 3 exp(-pi^2 x) (x > t): one exponential; the full coefficients are evaluated only on the
-// rare (< 0.6 %) continuation of the series.
+// or 3 exp(-pi^2 x) (x > t); the full coefficients are evaluated only on the rare (< 0.6 %)
+// continuation of the series.
 __device__ double pg_one(Rng& rng, const PgTilt& c) {
     for (int it = 0; it < 10000; ++it) {
         const uint4 r = rng.next4();
@@ -86,18 +105,23 @@ __device__ double pg_one(Rng& rng, const PgTilt& c) {
         double X;
         if (u1 < c.pmass) X = PG_TRUNC - log(u1 / c.pmass) / c.fz;       // u1 / pmass is U(0,1) given the branch
         else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) / (1.0 - c.pmass));
-        const double ratio = 3.0 * (X > PG_TRUNC ? exp(-PG_PI * PG_PI * X) : exp(-4.0 / X));
-        if (u2 <= 1.0 - ratio) return 0.25 * X;
+        const double arg = X > PG_TRUNC ? -PG_PI * PG_PI * X : -4.0 / X;
+        // u2 <= 1 - 3 exp(arg): FP32 screen (the threshold is within 2e-2 of 1), FP64 when borderline
+        const float thr = 1.0f - 3.0f * __expf((float)arg);
+        const float u2f = (float)u2;
+        bool accept;
+        if (u2f < thr - 2e-6f) accept = true;
+        else if (u2f > thr + 2e-6f) accept = false;
+        else accept = u2 <= 1.0 - 3.0 * exp(arg);
+        if (accept) return 0.25 * X;
         // continue the series from n = 2 with explicit coefficients
         double S = pg_acoef(0, X);
         const double Y = u2 * S;
         S -= pg_acoef(1, X);
-        bool rejected = false;
         for (int n = 2; n < 400; ++n) {
             if (n & 1) { S -= pg_acoef(n, X); if (Y <= S) return 0.25 * X; }
-            else { S += pg_acoef(n, X); if (Y > S) { rejected = true; break; } }
+            else { S += pg_acoef(n, X); if (Y > S) break; }
         }
-        (void)rejected;
     }
     return 0.25 * PG_TRUNC;
 }
@@ -206,6 +230,22 @@ void launch_rng_sample(int kind, double param, double* out, long long n, uint64_
 }
 
 // ---------------------------------------------------------------- negative-binomial R
+// atomicAdd with warp aggregation: lanes that target the same group are summed by a leader
+// (with rdims = (0,1,2) there is ONE group, and per-lane atomics on one address serialise)
+__device__ __forceinline__ void group_add(double* base, int g, double v, bool active) {
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(mask, g);
+    const int leader = __ffs(peers) - 1;
+    double sum = 0.0;
+    // fixed-order sum over the peer lanes
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        sum += __shfl_sync(peers, v, src);
+    }
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(base + g, sum);
+}
+
 // work layout (Rs = number of R entries):
 //   logR[Rs] cand[Rs] candlog[Rs] lg_cur[Rs] lg_cand[Rs] slog[Rs] ng[Rs]
 __device__ __forceinline__ int nb_group(const NbArgs& a, int i, int j, int t) {
@@ -215,31 +255,37 @@ __device__ __forceinline__ int nb_group(const NbArgs& a, int i, int j, int t) {
 // per cell: psi -> log(1-P); accumulate slog_g, n_g and lg_cur_g = sum lgamma(y + R_g)
 __global__ void nb_prepare_kernel(NbArgs a) {
     const int Rs = a.Rn * a.Rm * a.Rt;
-    double *logR = a.work, *lg_cur = a.work + 3 * Rs, *slog = a.work + 5 * Rs, *ng = a.work + 6 * Rs;
+    double *lg_cur = a.work + 3 * Rs, *slog = a.work + 5 * Rs, *ng = a.work + 6 * Rs;
     const long long cells = (long long)a.nloc * a.P;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
-        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
-        const int j = p / a.T, t = p - j * a.T;
-        const int g = nb_group(a, a.row_begin + il, j, t);
-        const double* y = a.Yraw + e * a.R;
-        int c = 0;
-        double lg = 0.0;
-        const double Rg = a.Rdisp[g];
-        for (int r = 0; r < a.R; ++r) {
-            double v = y[r];
-            if (v == v) { ++c; lg += lgamma(v + Rg); }
+    // block-uniform trip count: every lane reaches the warp-collective group_add
+    for (long long eb = (long long)blockIdx.x * blockDim.x; eb < cells; eb += (long long)gridDim.x * blockDim.x) {
+        const long long e = eb + threadIdx.x;
+        const bool in = e < cells;
+        int g = 0, c = 0;
+        double lg = 0.0, sl = 0.0;
+        if (in) {
+            const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+            const int j = p / a.T, t = p - j * a.T;
+            g = nb_group(a, a.row_begin + il, j, t);
+            const double* y = a.Yraw + e * a.R;
+            const double Rg = a.Rdisp[g];
+            for (int r = 0; r < a.R; ++r) {
+                double v = y[r];
+                if (v == v) { ++c; lg += lgamma(v + Rg); }
+            }
+            if (c) {
+                double psi = 0.0;
+                for (int k = 0; k < a.K; ++k) psi += a.W[(size_t)il * a.K + k] * a.V[(size_t)p * a.K + k];
+                psi = clampd(psi, -10.0, 10.0);
+                const double Pr = 1.0 / (1.0 + exp(-psi));      // ilogit as in utils.py:106-107
+                sl = c * log(1.0 - Pr);
+            }
         }
-        if (c) {
-            double psi = 0.0;
-            for (int k = 0; k < a.K; ++k) psi += a.W[(size_t)il * a.K + k] * a.V[(size_t)p * a.K + k];
-            psi = clampd(psi, -10.0, 10.0);
-            const double Pr = 1.0 / (1.0 + exp(-psi));      // ilogit as in utils.py:106-107
-            atomicAdd(&slog[g], c * log(1.0 - Pr));
-            atomicAdd(&ng[g], (double)c);
-            atomicAdd(&lg_cur[g], lg);
-        }
+        const bool act = in && c > 0;
+        group_add(slog, g, sl, act);
+        group_add(ng, g, (double)c, act);
+        group_add(lg_cur, g, lg, act);
     }
-    (void)logR;
 }
 
 __global__ void nb_init_kernel(NbArgs a) {
@@ -285,16 +331,21 @@ __global__ void nb_lgamma_kernel(NbArgs a) {
     const double* cand = a.work + Rs;
     double* lg_cand = a.work + 4 * Rs;
     const long long cells = (long long)a.nloc * a.P;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
-        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
-        const int j = p / a.T, t = p - j * a.T;
-        const int g = nb_group(a, a.row_begin + il, j, t);
-        const double* y = a.Yraw + e * a.R;
-        const double Rc = cand[g];
+    for (long long eb = (long long)blockIdx.x * blockDim.x; eb < cells; eb += (long long)gridDim.x * blockDim.x) {
+        const long long e = eb + threadIdx.x;
+        const bool in = e < cells;
+        int g = 0;
         double lg = 0.0;
         bool any = false;
-        for (int r = 0; r < a.R; ++r) { double v = y[r]; if (v == v) { lg += lgamma(v + Rc); any = true; } }
-        if (any) atomicAdd(&lg_cand[g], lg);
+        if (in) {
+            const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+            const int j = p / a.T, t = p - j * a.T;
+            g = nb_group(a, a.row_begin + il, j, t);
+            const double* y = a.Yraw + e * a.R;
+            const double Rc = cand[g];
+            for (int r = 0; r < a.R; ++r) { double v = y[r]; if (v == v) { lg += lgamma(v + Rc); any = true; } }
+        }
+        group_add(lg_cand, g, lg, in && any);
     }
 }
 

@@ -141,8 +141,8 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
         Pband[e] = s;
     }
 
-    double* Lrow = a.work_L + (size_t)jl * n * (kd + K + 1);
-    double* yg = a.work_y + (size_t)jl * 2 * n;      // [y (n) | 1 / diag(L) (n)]
+    double* Lrow = a.work_L + (size_t)jl * a.work_L_stride;
+    double* yg = a.work_y + (size_t)jl * a.work_y_stride;      // [y (n) | 1 / diag(L) (n)]
     const bool have_stats = a.stats != nullptr;     // nullptr: prior-only system (V initialisation)
     const double* stats0 = have_stats ? a.stats + (size_t)jg * T * nco : nullptr;
     const int mblk = tid / K;

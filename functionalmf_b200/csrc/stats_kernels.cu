@@ -348,7 +348,11 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
 // DMMA loop of chunk c (four rows per k-step, spread over the 8 warps), from a factor tile
 // that is prefetched two chunks ahead; Z is double buffered.  The tensor pipe no longer idles
 // during Z generation and one barrier per chunk replaces three.
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
+// UNI: the product and factor tiles form ONE list that is dealt to the column warps in runs of
+// CTM tiles (K = 32: 70 tiles over 8 warps -> 9 per warp, 2 idle slots instead of 10).  Slots
+// whose tile index can exceed the product range are "late" slots: they are product tiles for
+// every warp but the last one, whose late slots are factor tiles (or idle).
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI>
 __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a) {
     static_assert(WR * WC == 8, "Z generation inside the DMMA loop is laid out for 8 warps");
     constexpr int NT = 32 * WR * WC;
@@ -461,6 +465,9 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
 
     const int zoff_z = wc * ZPW * 8 + (lane >> 2);
     const int zoff_f = (nct_z + wc * FPW) * 8 + (lane >> 2);
+    static_assert(!UNI || (WC - 1) * CTM <= nct_z, "only the last column warp may own factor tiles");
+    const int zoff_u = wc * CTM * 8 + (lane >> 2);
+    const bool last_wc = wc == WC - 1;
 
     if (c_begin < c_end) {
         load_data(0, c_begin);
@@ -509,12 +516,25 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
                 }
             }
             const double* zrow = zcur + kl * zw;
+            if (UNI) {
+                double al[RT];                    // operand of the late slots: one select per k-step
 #pragma unroll
-            for (int ci = 0; ci < CTM; ++ci) {
-                const bool isz = ci < ZPW;
-                const double b = isz ? zrow[zoff_z + ci * 8] : zrow[zoff_f + (ci - ZPW) * 8];
+                for (int r = 0; r < RT; ++r) al[r] = last_wc ? as[r] : aw[r];
 #pragma unroll
-                for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+                for (int ci = 0; ci < CTM; ++ci) {
+                    const bool late = (WC - 1) * CTM + ci >= nct_z;        // compile-time
+                    const double b = zrow[zoff_u + ci * 8];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], late ? al[r] : aw[r], b);
+                }
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < CTM; ++ci) {
+                    const bool isz = ci < ZPW;
+                    const double b = isz ? zrow[zoff_z + ci * 8] : zrow[zoff_f + (ci - ZPW) * 8];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], isz ? aw[r] : as[r], b);
+                }
             }
             // four rows of the NEXT chunk's Z tile, issued in the shadow of the DMMAs above
             if (more) {
@@ -534,9 +554,16 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
         if (m < a.m_valid) {
 #pragma unroll
             for (int ci = 0; ci < CTM; ++ci) {
-                const bool isz = ci < ZPW;
-                const int tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
-                if (ci < ZPW + FPW && tl < (isz ? nct_z : nct_f)) {
+                bool isz, valid;
+                int tl;
+                if (UNI) {
+                    const int tix = wc * CTM + ci;
+                    isz = tix < nct_z; tl = isz ? tix : tix - nct_z; valid = tix < nct_z + nct_f;
+                } else {
+                    isz = ci < ZPW; tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
+                    valid = ci < ZPW + FPW && tl < (isz ? nct_z : nct_f);
+                }
+                if (valid) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int cc = tl * 8 + (lane & 3) * 2 + h;
@@ -583,7 +610,7 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
 
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX>
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI>
 static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double* sv, const double* F,
                                long long ld, int m_valid, double* out, cudaStream_t st) {
     StatsKArgs a;
@@ -591,7 +618,7 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
     a.K = p.K; a.L = p.L; a.nct_z = p.nct_z; a.nct_f = p.nct_f; a.zw = p.zw;
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
-    auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX>;
+    auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX, UNI>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -614,6 +641,7 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
 #define BTF_CFG3 128, 4, 2, 10, 32
 #define BTF_CFG4 32, 1, 8, 10, 16
 #define BTF_CFG5 128, 8, 1, 6, 32
+#define BTF_CFG4U 32, 1, 8, 9, 16      // K == 32 with the unified tile list (overlapped kernel)
 
 static int cfg_wc(int cfg) { return (cfg == 1 || cfg == 4) ? 8 : (cfg == 3 ? 2 : 1); }
 
@@ -632,6 +660,7 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
     const int WC = cfg_wc(p->cfg);
     // Z row width: every tile slot any warp may touch, rounded so that zw = 4 or 12 (mod 16)
     int need = std::max(nct, std::max(WC * cdiv(p->nct_z, WC), p->nct_z + WC * cdiv(p->nct_f, WC))) * 8;
+    if (p->cfg == 4) need = std::max(need, 8 * 9 * 8);     // unified list: 8 warps x 9 tile slots
     int zw = need;
     while (!((zw % 16) == 4 || (zw % 16) == 12)) ++zw;
     p->zw = zw;
@@ -683,7 +712,7 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
                                             : stats_smem_ovl<__VA_ARGS__, true, uint8_t>(K, p->zw)) \
                              : (weights_f64 ? stats_smem_ovl<__VA_ARGS__, false, double>(K, p->zw)  \
                                             : stats_smem_ovl<__VA_ARGS__, false, uint8_t>(K, p->zw)))
-        size_t so = p->cfg == 3 ? SMEM_OVL(BTF_CFG3) : (p->cfg == 4 ? SMEM_OVL(BTF_CFG4) : SMEM_OVL(BTF_CFG5));
+        size_t so = p->cfg == 3 ? SMEM_OVL(BTF_CFG3) : (p->cfg == 4 ? SMEM_OVL(BTF_CFG4U) : SMEM_OVL(BTF_CFG5));
 #undef SMEM_OVL
         if (so <= 220 * 1024) { p->overlap = 1; p->smem_bytes = so; }
     }
@@ -702,21 +731,21 @@ void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* 
             else launch_stats_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
         }                                                                                                        \
     } while (0)
-#define DISPATCH_OVL(KF, ...)                                                                                        \
-    do {                                                                                                             \
-        if (trans) {                                                                                                 \
-            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, true, double, KF>(p, wt, sv, F, ld, m_valid, out, st);  \
-            else launch_stats_ovl_t<__VA_ARGS__, true, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);             \
-        } else {                                                                                                     \
-            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, false, double, KF>(p, wt, sv, F, ld, m_valid, out, st); \
-            else launch_stats_ovl_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
-        }                                                                                                            \
+#define DISPATCH_OVL(KF, UNI_, ...)                                                                                        \
+    do {                                                                                                                   \
+        if (trans) {                                                                                                       \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, true, double, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);  \
+            else launch_stats_ovl_t<__VA_ARGS__, true, uint8_t, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);             \
+        } else {                                                                                                           \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, false, double, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_ovl_t<__VA_ARGS__, false, uint8_t, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);            \
+        }                                                                                                                  \
     } while (0)
     if (p.overlap) {
         switch (p.cfg) {
-            case 3: DISPATCH_OVL(16, BTF_CFG3); return;
-            case 4: DISPATCH_OVL(32, BTF_CFG4); return;
-            default: DISPATCH_OVL(8, BTF_CFG5); return;
+            case 3: DISPATCH_OVL(16, false, BTF_CFG3); return;
+            case 4: DISPATCH_OVL(32, true, BTF_CFG4U); return;
+            default: DISPATCH_OVL(8, false, BTF_CFG5); return;
         }
     }
 #undef DISPATCH_OVL
