@@ -3,7 +3,7 @@
 //
 // PG(1, z): Devroye's exact alternating-series sampler (Polson, Scott & Windle 2013,
 // Alg. 1; truncation t = 0.64).  PG(b, z): floor(b) such draws + truncated
-// sum-of-gammas for the fractional part (expected tail added back); b > 170: the
+// sum-of-gammas for the fractional part (tail replaced by its moment-matched normal); b > 170: the
 // moment-matched normal approximation (the rule of the hybrid sampler the
 // reference's third-party dependency implements).  All randomness is Philox,
 // keyed by (seed, sweep, global cell index).
@@ -14,7 +14,7 @@ namespace btf {
 #define PG_TRUNC 0.64
 #define PG_PI 3.14159265358979323846
 #define PG_NORMAL_B 170.0
-#define PG_SERIES 200
+#define PG_SERIES 32
 
 __device__ __forceinline__ double log_phi(double x) {
     if (x > -5.0) return log(0.5 * erfc(-x * 0.70710678118654752440));
@@ -150,14 +150,21 @@ __device__ double pg_draw(Rng& rng, double b, double z) {
     double acc = 0.0;
     for (int k = 0; k < bi; ++k) acc += pg_one(rng, c);
     if (bf > 1e-12) {
-        double s = 0.0, dsum = 0.0;
+        // fractional part: PG(bf, z) = 2 sum_k g_k / d_k, g_k ~ Gamma(bf, 1), d_k = 4 pi^2 (k-1/2)^2 + z^2.
+        // The first PG_SERIES terms are drawn; the remainder (about 1 % of the mass, a sum of many
+        // small independent terms) is replaced by a normal with its exact mean and variance.
+        double s = 0.0, d1 = 0.0, d2 = 0.0;
         for (int k = 1; k <= PG_SERIES; ++k) {
-            double km = k - 0.5;
-            double d = 4.0 * PG_PI * PG_PI * km * km + z * z;
-            s += rng.gamma(bf) / d;
-            dsum += 1.0 / d;
+            const double km = k - 0.5;
+            const double d = 4.0 * PG_PI * PG_PI * km * km + z * z;
+            const double di = 1.0 / d;
+            s += rng.gamma(bf) * di;
+            d1 += di;
+            d2 += di * di;
         }
-        acc += 2.0 * s + (pg_mean(bf, z) - 2.0 * bf * dsum);
+        const double tail_mean = pg_mean(bf, z) - 2.0 * bf * d1;
+        const double tail_var = fmax(pg_var(bf, z) - 4.0 * bf * d2, 0.0);
+        acc += 2.0 * s + fmax(tail_mean + sqrt(tail_var) * rng.normal(), 0.0);
     }
     return acc;
 }

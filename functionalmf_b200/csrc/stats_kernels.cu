@@ -642,6 +642,7 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
 #define BTF_CFG4 32, 1, 8, 10, 16
 #define BTF_CFG5 128, 8, 1, 6, 32
 #define BTF_CFG4U 32, 1, 8, 9, 16      // K == 32 with the unified tile list (overlapped kernel)
+#define BTF_CFG3A 128, 8, 1, 19, 32    // K == 16 alternative: 8x1 warps, every warp owns all 19 tiles (no idle slot)
 
 static int cfg_wc(int cfg) { return (cfg == 1 || cfg == 4) ? 8 : (cfg == 3 ? 2 : 1); }
 
@@ -742,6 +743,8 @@ void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* 
         }                                                                                                                  \
     } while (0)
     if (p.overlap) {
+        static const bool k16_alt = getenv("BTF_STATS_K16_ALT") != nullptr;
+        if (p.cfg == 3 && k16_alt) { DISPATCH_OVL(16, false, BTF_CFG3A); return; }
         switch (p.cfg) {
             case 3: DISPATCH_OVL(16, false, BTF_CFG3); return;
             case 4: DISPATCH_OVL(32, true, BTF_CFG4U); return;
