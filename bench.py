@@ -328,6 +328,10 @@ def bench_ours(args):
         hbm_src = 'MEASURED_PEAKS.json' if hbm_peak else 'fallback (B200_PROFILING.md)'
         hbm_peak = hbm_peak or 6650.0
         bytes_stats = 2.0 * cells * 9.0 / world
+        # DRAM traffic per launch of the dominant kernel from the ncu --set full capture of this
+        # workload (profiles/r1_ncu_stats_r1_final_summary.txt: rows 2.425 GB read + 0.027 GB written,
+        # columns 2.418 GB + 0.143 GB); algorithmic bytes per launch are cells * 9 B = 2.416 GB
+        traffic = 2.5063e9 if (args.workload == 'c2' and world == 1) else None
         out = {
             'metric': 'Gibbs sweeps/sec', 'value': args.steps / (ms * 1e-3), 'unit': 'sweeps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
@@ -341,7 +345,7 @@ def bench_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak if peak > 0 else None, 'traffic': None,
+                         'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
                          'kernel': 'stats_kernel (row + column sufficient-statistic contractions, FP64 DMMA)',
                          'flops_per_sweep_per_gpu': flops_stats, 'kernel_ms_per_sweep': stats_ms,
                          'peak_source': 'btf_fp64_peak micro-benchmark in this run (DMMA %.2f, DFMA %.2f TFLOP/s); '
