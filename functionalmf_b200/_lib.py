@@ -48,6 +48,7 @@ class Config(C.Structure):
         ('world_size', C.c_int32), ('rank', C.c_int32),
         ('resid_direct', C.c_int32), ('use_graph', C.c_int32),
         ('stats_splits_row', C.c_int32), ('stats_splits_col', C.c_int32),
+        ('clip_prior_precision', C.c_int32),
     ]
 
 

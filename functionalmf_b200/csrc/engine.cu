@@ -644,7 +644,7 @@ static int enqueue_sweep(btf_engine* e) {
             ScalarStepArgs sa{e->scal, c.seed, c.nu2_a, c.nu2_b, inj(e, "g_nu2")};
             launch_nu2(sa, st); e->launches++;
         }
-    } else {
+    } else if ((mask & BTF_SAMPLE_NU2) || inj(e, "omega")) {
         const double* om = inj(e, "omega");
         if (om) {
             cudaMemcpy2DAsync(e->omega, (size_t)e->Ppad * 8, om, (size_t)e->P * 8, (size_t)e->P * 8, e->nloc,
@@ -728,6 +728,7 @@ static int enqueue_sweep(btf_engine* e) {
             ba.stats = e->col_stats; ba.nsplit = nsplit; ba.split_stride = e->plan_col.out_elems_per_split;
             ba.col_begin = c.col_begin; ba.ncols_loc = e->Mloc; ba.T = e->T; ba.K = e->K; ba.order = e->order; ba.RD = e->RD;
             ba.homoskedastic = gauss ? 1 : 0; ba.scal = e->scal; ba.Tau2 = e->Tau2;
+            ba.prior_clip = c.clip_prior_precision ? c.stability : 0.0;
             ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
             ba.V = e->V; ba.z_inject = inj(e, "z_V"); ba.seed = c.seed;
             ba.work_L = e->work_L; ba.work_y = e->work_y;
@@ -812,7 +813,10 @@ static int one_sweep(btf_engine* e) {
 
 static int pre_run(btf_engine* e) {
     if (!e) return set_err(BTF_EINVAL, "null engine");
-    if (!e->has_data) return set_err(BTF_ESTATE, "no data: call btf_set_data_* first");
+    // the hyper-parameter steps (sigma2, Tau2, lam2) only read the factors: no data needed for them
+    const int needs_data = BTF_SAMPLE_NU2 | BTF_SAMPLE_W | BTF_SAMPLE_V | BTF_SAMPLE_R;
+    if (!e->has_data && ((e->cfg.sample_mask & needs_data) || e->cfg.likelihood != BTF_GAUSSIAN))
+        return set_err(BTF_ESTATE, "no data: call btf_set_data_* first");
     CK(cudaSetDevice(e->cfg.device));
     int rc = ensure_data_reduced(e);
     if (rc) return rc;

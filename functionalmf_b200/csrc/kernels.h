@@ -60,6 +60,7 @@ struct BandSolveArgs {
     int nsplit; size_t split_stride;
     int col_begin, ncols_loc, T, K, order, RD;
     int homoskedastic;     // 1: scale statistics by 1/nu2
+    double prior_clip;     // > 0: clip 1/(lam2 tau2) to [prior_clip, 1/prior_clip] (factor.py:767)
     Scalars* scal;
     const double* Tau2;    // [M][RD]
     const int* pm_ptr; const int* pm_row; const double* pm_coef;   // CSR of Delta^T diag Delta band

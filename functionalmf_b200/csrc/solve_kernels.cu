@@ -132,7 +132,11 @@ __global__ void band_solve_kernel(BandSolveArgs a) {
 
     const double scale = a.homoskedastic ? 1.0 / a.scal->nu2 : 1.0;
     const double lam2 = a.scal->lam2;
-    for (int r = tid; r < a.RD; r += NT) linv[r] = 1.0 / (lam2 * a.Tau2[(size_t)jg * a.RD + r]);
+    for (int r = tid; r < a.RD; r += NT) {
+        double pv = 1.0 / (lam2 * a.Tau2[(size_t)jg * a.RD + r]);
+        if (a.prior_clip > 0.0) pv = fmin(fmax(pv, a.prior_clip), 1.0 / a.prior_clip);
+        linv[r] = pv;
+    }
     if (tid == 0) fail_flag = 0;
     __syncthreads();
     for (int e = tid; e < T * (q + 1); e += NT) {

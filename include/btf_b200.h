@@ -66,6 +66,7 @@ typedef struct btf_config {
     int32_t resid_direct;              /* 1: always recompute the nu2 residual by a full pass */
     int32_t use_graph;                 /* 1: replay the sweep as a CUDA graph when possible */
     int32_t stats_splits_row, stats_splits_col;  /* 0 = auto */
+    int32_t clip_prior_precision;      /* 1: 1/(lam2 Tau2) clipped to [stability, 1/stability] (factor.py:767) */
 } btf_config;
 
 void btf_config_default(btf_config* cfg);
