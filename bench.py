@@ -291,6 +291,7 @@ def bench_ours(args):
         d2h = (res_W[0].nbytes + res_V[0].nbytes + res_T[0].nbytes + res_S[0].nbytes)
         e2e = {'value': K_e2e / e2e_s, 'unit': 'sweeps/s', 'h2d_bytes_per_step': Y.nbytes / float(K_e2e),
                'd2h_bytes_per_step': d2h, 'seconds': e2e_s, 'upload_seconds': t_up,
+               'host_buffers': sorted(set(how for _, how in __import__('functionalmf_b200.engine', fromlist=['x']).PINNED_LOG)),
                'includes': 'H2D of Y (%.2f GB per rank, once) + pre-reduction, %d sweeps, D2H of W,V,Tau2,scalars '
                            'every sweep' % (Y.nbytes / 1e9, K_e2e)}
 

@@ -75,6 +75,8 @@ SIGNATURES = {
     'btf_init_state': (C.c_int, [_P, C.c_int32]),
     'btf_host_alloc': (_P, [C.c_size_t]),
     'btf_host_free': (None, [_P]),
+    'btf_host_register': (C.c_int, [_P, C.c_size_t]),
+    'btf_host_unregister': (C.c_int, [_P]),
     'btf_sweep_timed': (C.c_int, [_P, C.c_int32, _D]),
     'btf_inject_noise': (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     'btf_enable_diag': (C.c_int, [_P, C.c_int32]),

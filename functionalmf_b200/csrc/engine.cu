@@ -941,6 +941,17 @@ void* btf_host_alloc(size_t bytes) {
     return p;
 }
 void btf_host_free(void* p) { if (p) cudaFreeHost(p); }
+// page-lock an existing host allocation in place (fallback when a fresh pinned allocation fails)
+int btf_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return set_err(BTF_EINVAL, "bad arguments");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(BTF_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return BTF_OK;
+}
+int btf_host_unregister(void* p) {
+    if (p && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    return BTF_OK;
+}
 
 // Initial state drawn from the priors on the device (factor.py:230-253, 293-304, 560-563).
 // init_mask bits: 1 sigma2, 2 lam2(+lam2_a), 4 nu2, 8 Tau2(+a,b,c), 16 W, 32 V, 64 R

@@ -14,17 +14,28 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
 
 
+PINNED_LOG = []      # (nbytes, how) for every pinned_empty call: 'alloc', 'registered' or 'pageable'
+
+
 def pinned_empty(shape):
-    """float64 array in page-locked host memory (falls back to pageable memory)."""
+    """float64 array in page-locked host memory: a fresh pinned allocation, else a pageable
+    array page-locked in place, else (logged in PINNED_LOG) plain pageable memory."""
     lib = L.load()
     n = int(np.prod(shape)) if len(shape) else 1
     nbytes = max(n, 1) * 8
     p = lib.btf_host_alloc(nbytes)
-    if not p:
-        return np.empty(shape, dtype=np.float64)
-    buf = (C.c_double * max(n, 1)).from_address(p)
-    arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
-    weakref.finalize(buf, lib.btf_host_free, p)
+    if p:
+        buf = (C.c_double * max(n, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+        weakref.finalize(buf, lib.btf_host_free, p)
+        PINNED_LOG.append((nbytes, 'alloc'))
+        return arr
+    arr = np.empty(shape, dtype=np.float64)
+    if arr.size and lib.btf_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes) == 0:
+        weakref.finalize(arr, lib.btf_host_unregister, C.c_void_p(arr.ctypes.data))
+        PINNED_LOG.append((nbytes, 'registered'))
+    else:
+        PINNED_LOG.append((nbytes, 'pageable'))
     return arr
 
 

@@ -116,6 +116,8 @@ int btf_init_state(btf_engine* e, int32_t init_mask);
 /* pinned host memory for result arrays (so sample collection overlaps the next sweep) */
 void* btf_host_alloc(size_t bytes);
 void  btf_host_free(void* p);
+int   btf_host_register(void* p, size_t bytes);     /* page-lock an existing allocation in place */
+int   btf_host_unregister(void* p);
 /* nsweeps sweeps bracketed by CUDA events on the engine's stream; *ms_out = elapsed ms */
 int btf_sweep_timed(btf_engine* e, int32_t nsweeps, double* ms_out);
 
