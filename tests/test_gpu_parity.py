@@ -296,3 +296,88 @@ def test_not_positive_definite_raises():
     with pytest.raises(NotPositiveDefiniteError):
         eng.sweep(1)
     eng.close()
+
+
+@pytest.mark.parametrize('shape', [(150, 6, 9, 8, 1), (260, 5, 8, 16, 2), (140, 4, 7, 32, 1), (70, 5, 6, 5, 2)])
+def test_binomial_sweep_vs_oracle(shape):
+    """Heteroskedastic (Polya-Gamma) path with injected omega: the f64-weight statistics kernels
+    (compile-time K = 8 / 16 / 32 and the runtime-K variant) against the oracle."""
+    from oracle import btf_oracle as O
+    from functionalmf_b200.engine import Engine
+    N, M, T, K, order = shape
+    rs = np.random.RandomState(77 + K)
+    W = rs.normal(size=(N, K)) * 0.5
+    W[np.triu_indices(K, k=1)] = 0
+    V = rs.normal(size=(M, T, K)).cumsum(axis=1) * 0.2
+    Nt = rs.randint(1, 9, size=(N, M, T)).astype(float)
+    Ys = rs.binomial(Nt.astype(int), 1 / (1 + np.exp(-np.einsum('nk,mtk->nmt', W, V)))).astype(float)
+    miss = rs.random_sample(Ys.shape) < 0.1
+    Ys[miss] = np.nan
+    Nt[miss] = np.nan
+    eng = Engine(N, M, T, nembeds=K, tf_order=order, likelihood=1, seed=9)
+    Delta = eng.get('Delta')
+    RD = Delta.shape[0]
+    st = _random_state(rs, N, M, T, K, RD, W, V)
+    noise = _random_noise(rs, N, M, T, K, RD)
+    del noise['g_nu2']
+    noise['omega'] = np.where(miss, 0.0, rs.gamma(2.0, 0.15, size=(N, M, T)) + 0.02)
+    cfg = dict(K=K, order=order, Delta=Delta, nu2_a=0.1, nu2_b=0.1, sigma2_a=0.1, sigma2_b=0.1,
+               stability=1e-6, force_psd=True, force_psd_eps=1e-6, force_psd_attempts=4, ref_compat=True)
+    want = O.binomial_sweep(st, Ys, Nt, noise, cfg)
+    eng.set_data_binomial(Ys, Nt)
+    eng.enable_diag(True)
+    load_state(eng, st, gaussian=False)
+    inject_all(eng, noise)
+    eng.sweep(1)
+    cw, sw = O.binomial_weights(Ys, Nt, noise['omega'])
+    A, b = O.row_stats(st['V'], cw, sw)
+    Lp = K * (K + 1) // 2
+    il = np.tril_indices(K)
+    rstat = eng.diag('row_stats')
+    assert normerr(rstat[:, :Lp], A[:, il[0], il[1]]) < TOL
+    assert normerr(rstat[:, Lp:], b) < TOL
+    Ac, bc = O.col_stats(want['W'], cw, sw)
+    cstat = eng.diag('col_stats')
+    assert normerr(cstat[:, :Lp], Ac.reshape(M * T, K, K)[:, il[0], il[1]]) < TOL
+    assert normerr(cstat[:, Lp:], bc.reshape(M * T, K)) < TOL
+    for k in ('sigma2', 'lam2', 'lam2_a'):
+        assert relerr(eng.get_scalar(k), want[k]) < TOL, k
+    assert relerr(eng.get('Tau2'), want['Tau2']) < TOL
+    assert normerr(eng.get('W'), want['W']) < 1e-9
+    Vn, dV = O.step_V(want['W'], st['V'], cw, sw, Delta, want['lam2'], want['Tau2'], noise['z_V'], order,
+                      want_diag=True)
+    Vg = eng.get('V')
+    for j in range(M):
+        Qd = O.band_to_dense_lower(dV['band'][j])
+        Qd = Qd + np.tril(Qd, -1).T
+        tol = max(TOL, 50 * np.linalg.cond(Qd) * EPS)
+        assert normerr(Vg[j], Vn[j]) < tol, j
+    # kappa and the trial counts the PG step sees
+    kap = eng.get('kappa')
+    assert np.allclose(kap[~miss], (Ys - Nt / 2)[~miss]) and np.all(kap[miss] == 0)
+    eng.close()
+
+
+def test_lam2_all_columns_mode_vs_oracle():
+    """ref_compat=False: rate summed over all columns plus the 1/lam2_a prior term."""
+    from oracle import btf_oracle as O
+    from functionalmf_b200.engine import Engine
+    N, M, T, R, K, order = 30, 7, 11, 2, 4, 2
+    rs = np.random.RandomState(12)
+    W, V, Y = _random_problem(rs, N, M, T, R, K)
+    eng = Engine(N, M, T, nembeds=K, tf_order=order, seed=1, ref_compat_lam2=0)
+    Delta = eng.get('Delta')
+    RD = Delta.shape[0]
+    st = _random_state(rs, N, M, T, K, RD, W, V)
+    noise = _random_noise(rs, N, M, T, K, RD)
+    eng.set_data_gaussian(Y)
+    load_state(eng, st)
+    inject_all(eng, noise)
+    eng.set_sample_mask(4 | 8)           # Tau2 and lam2
+    eng.sweep(1)
+    Tau2 = O.step_tau2(st['V'], Delta, st['lam2'], st['Tau2_a'], st['Tau2_b'], st['Tau2_c'], noise['g_tau'], K)[0]
+    lam2, lam2_a, rate, shape = O.step_lam2(st['V'], Delta, Tau2, st['lam2_a'], noise['g_lam'], K, ref_compat=False)
+    assert relerr(eng.get_scalar('lam2'), lam2) < TOL and relerr(eng.get_scalar('lam2_a'), lam2_a) < TOL
+    got = eng.diag('lam2_rate')
+    assert relerr(got[0], rate) < TOL and relerr(got[1], shape) < TOL
+    eng.close()
