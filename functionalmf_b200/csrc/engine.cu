@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -58,6 +59,7 @@ struct btf_engine {
     bool has_data = false, data_reduced = false;
     // NB dispersion
     double* Rdisp = nullptr; int Rn = 1, Rm = 1, Rt = 1; double* nb_work = nullptr;
+    double* nb_hist = nullptr; int nb_hist_stride = 0;   // count histograms per R group (integer counts)
     // penalty
     std::vector<double> delta;   // dense [RD][T]
     int *d_start = nullptr, *d_width = nullptr; double* d_coef = nullptr; int d_maxw = 0;
@@ -294,7 +296,7 @@ void btf_destroy(btf_engine* e) {
     free_graph(e);
     if (e->shard) nccl_shard_destroy(e->shard);
     void* ptrs[] = {e->W, e->V, e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c, e->scal, e->cnt, e->S, e->ntr, e->omega,
-                    e->Yraw, e->Rdisp, e->nb_work, e->d_start, e->d_width, e->d_coef, e->pm_ptr, e->pm_row, e->pm_coef,
+                    e->Yraw, e->Rdisp, e->nb_work, e->nb_hist, e->d_start, e->d_width, e->d_coef, e->pm_ptr, e->pm_row, e->pm_coef,
                     e->row_stats, e->col_stats, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -420,6 +422,30 @@ int btf_set_data_negbin(btf_engine* e, const double* Y, int32_t nreps) {
     if (e->nb_work) { CK(cudaFree(e->nb_work)); e->nb_work = nullptr; }
     const size_t rsize = (size_t)e->Rn * e->Rm * e->Rt;
     CK(dev_alloc(&e->nb_work, 8 * rsize + 64));
+    // count histograms for the fused MH chain (integer counts of moderate range only)
+    if (e->nb_hist) { CK(cudaFree(e->nb_hist)); e->nb_hist = nullptr; }
+    e->nb_hist_stride = 0;
+    {
+        unsigned long long* scan = nullptr;
+        CK(dev_alloc(&scan, 2));
+        launch_nb_scan(e->Yraw, (long long)total, scan, e->stream);
+        unsigned long long h[2];
+        CK(cudaMemcpyAsync(h, scan, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaFree(scan));
+        const size_t vstride = (size_t)h[0] + 1;
+        if (!h[1] && vstride * rsize <= ((size_t)1 << 24) && !getenv("BTF_NB_NO_HIST")) {
+            CK(dev_alloc(&e->nb_hist, vstride * rsize));
+            e->nb_hist_stride = (int)vstride;
+            NbArgs nb;
+            memset(&nb, 0, sizeof(nb));
+            nb.Yraw = e->Yraw; nb.nloc = e->nloc; nb.P = e->P; nb.R = nreps; nb.M = e->M; nb.T = e->T; nb.K = e->K;
+            nb.row_begin = e->cfg.row_begin; nb.Rn = e->Rn; nb.Rm = e->Rm; nb.Rt = e->Rt; nb.hist = e->nb_hist;
+            launch_nb_hist(nb, (int)vstride, e->stream);
+            CK(cudaStreamSynchronize(e->stream));
+            e->launches += 2;
+        }
+    }
     e->has_data = true; e->data_reduced = true;
     return BTF_OK;
 }
@@ -626,7 +652,8 @@ static int enqueue_sweep(btf_engine* e) {
         nb.z_inject = inj(e, "z_R"); nb.u_inject = inj(e, "u_R");
         nb.scal = e->scal; nb.seed = c.seed; nb.work = e->nb_work;
         nb.obs = e->cnt; nb.kappa = e->S; nb.ntr = e->ntr;
-        launch_nb_update(nb, st); e->launches += nb.nmh > 0 ? 2 * nb.nmh + 4 : 1;
+        nb.hist = e->nb_hist; nb.hist_stride = e->nb_hist_stride;
+        launch_nb_update(nb, st); e->launches += nb.nmh > 0 ? (nb.hist ? 4 : 2 * nb.nmh + 4) : 1;
     }
     if (gauss) {
         if (mask & BTF_SAMPLE_NU2) {

@@ -141,7 +141,10 @@ struct NbArgs {
     Scalars* scal; uint64_t seed;
     double* work;            // scratch [>= 4 * Rsize + nblocks * Rsize ...]
     uint8_t* obs; double* kappa; double* ntr;         // outputs of the pseudo-count refresh
+    double* hist; int hist_stride;                    // per-group count histogram [Rs][hist_stride] or nullptr
 };
+void launch_nb_scan(const double* Y, long long n, unsigned long long* out, cudaStream_t st);
+void launch_nb_hist(const NbArgs& a, int vstride, cudaStream_t st);
 // R | rest by nmh random-walk MH steps on log R, then N = sum_r (y + R), kappa = sum_r y - N/2
 // (factor.py:513-554, 494-511)
 void launch_nb_update(const NbArgs& a, cudaStream_t st);

@@ -278,7 +278,7 @@ __global__ void nb_prepare_kernel(NbArgs a) {
             const double Rg = a.Rdisp[g];
             for (int r = 0; r < a.R; ++r) {
                 double v = y[r];
-                if (v == v) { ++c; lg += lgamma(v + Rg); }
+                if (v == v) { ++c; if (!a.hist) lg += lgamma(v + Rg); }
             }
             if (c) {
                 double psi = 0.0;
@@ -291,7 +291,7 @@ __global__ void nb_prepare_kernel(NbArgs a) {
         const bool act = in && c > 0;
         group_add(slog, g, sl, act);
         group_add(ng, g, (double)c, act);
-        group_add(lg_cur, g, lg, act);
+        if (!a.hist) group_add(lg_cur, g, lg, act);
     }
 }
 
@@ -374,6 +374,89 @@ __global__ void nb_counts_kernel(NbArgs a) {
     }
 }
 
+// ---- count-histogram form of the MH loop: sum_e lgamma(y_e + r) = sum_v hist_g[v] lgamma(v + r)
+// (the counts are small non-negative integers and do not change between sweeps), so the whole
+// nmh-step chain of a group runs in ONE block without touching the data tensor again.
+__global__ void nb_scan_kernel(const double* __restrict__ Y, long long n, unsigned long long* out) {
+    // out[0] = max value (as integer), out[1] = 1 if any observed entry is negative / non-integer / huge
+    unsigned long long mx = 0, bad = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const double v = Y[e];
+        if (v == v) {
+            if (v < 0.0 || v > 1e9 || v != floor(v)) bad = 1;
+            else mx = max(mx, (unsigned long long)v);
+        }
+    }
+    atomicMax(&out[0], mx);
+    if (bad) atomicMax(&out[1], 1ull);
+}
+
+void launch_nb_scan(const double* Y, long long n, unsigned long long* out, cudaStream_t st) {
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    nb_scan_kernel<<<nb, 256, 0, st>>>(Y, n, out);
+}
+
+__global__ void nb_hist_kernel(NbArgs a, int vstride) {
+    const long long cells = (long long)a.nloc * a.P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
+        const int il = (int)(e / a.P), p = (int)(e - (long long)il * a.P);
+        const int j = p / a.T, t = p - j * a.T;
+        const int g = nb_group(a, a.row_begin + il, j, t);
+        const double* y = a.Yraw + e * a.R;
+        for (int r = 0; r < a.R; ++r) {
+            const double v = y[r];
+            if (v == v) atomicAdd(&a.hist[(size_t)g * vstride + (int)v], 1.0);
+        }
+    }
+}
+
+void launch_nb_hist(const NbArgs& a, int vstride, cudaStream_t st) {
+    const long long cells = (long long)a.nloc * a.P;
+    int nb = (int)((cells + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    nb_hist_kernel<<<nb, 256, 0, st>>>(a, vstride);
+}
+
+__global__ void __launch_bounds__(256) nb_mh_hist_kernel(NbArgs a, int vstride) {
+    __shared__ double sh[40];
+    const int Rs = a.Rn * a.Rm * a.Rt;
+    const int g = blockIdx.x;
+    const double* hist = a.hist + (size_t)g * vstride;
+    const double slog = a.work[5 * Rs + g], ng = a.work[6 * Rs + g];
+    const unsigned long long sweep = a.scal->sweep;
+    auto lgsum = [&](double r) -> double {
+        double acc = 0.0;
+        for (int v = threadIdx.x; v < vstride; v += blockDim.x) {
+            const double h = hist[v];
+            if (h != 0.0) acc += h * lgamma((double)v + r);
+        }
+        acc = block_sum(acc, sh);
+        if (threadIdx.x == 0) sh[36] = acc;
+        __syncthreads();
+        return sh[36];
+    };
+    double R = a.Rdisp[g], logR = log(R);
+    double lg_cur = lgsum(R);
+    for (int s = 0; s < a.nmh; ++s) {
+        double z;
+        if (a.z_inject) z = a.z_inject[(size_t)s * Rs + g];
+        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s) * Rs + g); z = rng.normal(); }
+        const double lc = logR + a.rpropstdev * z, Rc = exp(lc);
+        const double lg_cand = lgsum(Rc);
+        const double dprior = -(lc * lc - logR * logR) / (2.0 * a.rstdev * a.rstdev);
+        const double ll = lg_cand - lg_cur - ng * (lgamma(Rc) - lgamma(R)) + (Rc - R) * slog;
+        const double prob = exp(clampd(dprior + ll, -10.0, 1.0));
+        double u;
+        if (a.u_inject) u = a.u_inject[(size_t)s * Rs + g];
+        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s + 1) * Rs + g); u = rng.uniform(); }
+        if (u <= prob && Rc > 1.0) { R = Rc; logR = lc; lg_cur = lg_cand; }     // block-uniform
+    }
+    if (threadIdx.x == 0) a.Rdisp[g] = R;
+}
+
 void launch_nb_update(const NbArgs& a, cudaStream_t st) {
     const int Rs = a.Rn * a.Rm * a.Rt;
     const long long cells = (long long)a.nloc * a.P;
@@ -381,7 +464,11 @@ void launch_nb_update(const NbArgs& a, cudaStream_t st) {
     if (nb > 148 * 8) nb = 148 * 8;
     if (nb < 1) nb = 1;
     const int gb = (Rs + 127) / 128;
-    if (a.nmh > 0) {
+    if (a.nmh > 0 && a.hist) {
+        nb_init_kernel<<<gb, 128, 0, st>>>(a);
+        nb_prepare_kernel<<<nb, 256, 0, st>>>(a);
+        nb_mh_hist_kernel<<<Rs, 256, 0, st>>>(a, a.hist_stride);
+    } else if (a.nmh > 0) {
         nb_init_kernel<<<gb, 128, 0, st>>>(a);
         nb_prepare_kernel<<<nb, 256, 0, st>>>(a);
         for (int s = 0; s < a.nmh; ++s) {
