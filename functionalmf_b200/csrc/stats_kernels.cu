@@ -352,9 +352,13 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel(StatsKArgs a) {
 // CTM tiles (K = 32: 70 tiles over 8 warps -> 9 per warp, 2 idle slots instead of 10).  Slots
 // whose tile index can exceed the product range are "late" slots: they are product tiles for
 // every warp but the last one, whose late slots are factor tiles (or idle).
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI>
+// NH > 1 (implies UNI): the column tiles are split into NH parts handled by different CTAs
+// (blockIdx.z) that share the data tile through L2; each CTA generates only its part of Z, so a
+// twice as tall row tile fits and the generation / barrier cost per DMMA halves (K = 32).
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI, int NH>
 __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a) {
     static_assert(WR * WC == 8, "Z generation inside the DMMA loop is laid out for 8 warps");
+    static_assert(NH == 1 || UNI, "column parts use the unified tile list");
     constexpr int NT = 32 * WR * WC;
     constexpr int RT = BM / 8 / WR;
     using G = TileGeom<TRANS, WT, BM, KC>;
@@ -363,8 +367,12 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
     constexpr int K = KFIX, L = K * (K + 1) / 2;
     constexpr int nct_z = cdiv(L, 8), nct_f = cdiv(K, 8);
     constexpr int ZPW = cdiv(nct_z, WC), FPW = cdiv(nct_f, WC);
-    constexpr int ncw = (nct_z + nct_f) * 8;
-    constexpr int CZ = cdiv(ncw, 32), CZH = (CZ + 1) / 2;
+    constexpr int nct = nct_z + nct_f;
+    constexpr int TP = cdiv(nct, NH);                    // column tiles per part
+    const int part = NH > 1 ? blockIdx.z : 0;
+    const int gcol0 = part * TP * 8;                     // first global generated column of this part
+    const int ncw = (min(nct, (part + 1) * TP) - part * TP) * 8;   // generated columns held by this CTA
+    constexpr int CZ = cdiv(TP * 8, 32), CZH = (CZ + 1) / 2;
     constexpr int fbytes = ((KC * K * 8) + 15) & ~15;
     constexpr int dbytes = G::WBYTES + G::SBYTES;
     const int zw = a.zw;
@@ -383,9 +391,10 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
     int zcode[CZ];
 #pragma unroll
     for (int q = 0; q < CZ; ++q) {
-        int c = lane + 32 * q;
+        const int cl = lane + 32 * q;                    // local column of this CTA's Z tile
+        const int c = gcol0 + cl;                        // global generated column
         int code = 0;
-        if (c < ncw) {
+        if (cl < ncw) {
             if (c < nct_z * 8) {
                 if (c < L) {
                     int k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
@@ -465,9 +474,10 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
 
     const int zoff_z = wc * ZPW * 8 + (lane >> 2);
     const int zoff_f = (nct_z + wc * FPW) * 8 + (lane >> 2);
-    static_assert(!UNI || (WC - 1) * CTM <= nct_z, "only the last column warp may own factor tiles");
+    static_assert(!UNI || (NH - 1) * TP + (WC - 1) * CTM <= nct_z,
+                  "only the last column warp of the last part may own factor tiles");
     const int zoff_u = wc * CTM * 8 + (lane >> 2);
-    const bool last_wc = wc == WC - 1;
+    const bool last_wc = wc == WC - 1 && part == NH - 1;
 
     if (c_begin < c_end) {
         load_data(0, c_begin);
@@ -522,7 +532,7 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
                 for (int r = 0; r < RT; ++r) al[r] = last_wc ? as[r] : aw[r];
 #pragma unroll
                 for (int ci = 0; ci < CTM; ++ci) {
-                    const bool late = (WC - 1) * CTM + ci >= nct_z;        // compile-time
+                    const bool late = (NH - 1) * TP + (WC - 1) * CTM + ci >= nct_z;        // compile-time
                     const double b = zrow[zoff_u + ci * 8];
 #pragma unroll
                     for (int r = 0; r < RT; ++r) dmma(acc[r][ci][0], acc[r][ci][1], late ? al[r] : aw[r], b);
@@ -557,8 +567,8 @@ __global__ void __launch_bounds__(32 * WR* WC, 1) stats_kernel_ovl(StatsKArgs a)
                 bool isz, valid;
                 int tl;
                 if (UNI) {
-                    const int tix = wc * CTM + ci;
-                    isz = tix < nct_z; tl = isz ? tix : tix - nct_z; valid = tix < nct_z + nct_f;
+                    const int tloc = wc * CTM + ci, tix = part * TP + tloc;
+                    isz = tix < nct_z; tl = isz ? tix : tix - nct_z; valid = tloc < TP && tix < nct;
                 } else {
                     isz = ci < ZPW; tl = isz ? wc * ZPW + ci : wc * FPW + (ci - ZPW);
                     valid = ci < ZPW + FPW && tl < (isz ? nct_z : nct_f);
@@ -610,7 +620,7 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
 
-template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI>
+template <int BM, int WR, int WC, int CTM, int KC, bool TRANS, typename WT, int KFIX, bool UNI, int NH>
 static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double* sv, const double* F,
                                long long ld, int m_valid, double* out, cudaStream_t st) {
     StatsKArgs a;
@@ -618,13 +628,13 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
     a.K = p.K; a.L = p.L; a.nct_z = p.nct_z; a.nct_f = p.nct_f; a.zw = p.zw;
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
-    auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX, UNI>;
+    auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX, UNI, NH>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         attr_set = true;
     }
-    dim3 grid(p.mtiles, p.nsplit);
+    dim3 grid(p.mtiles, p.nsplit, NH);
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
 
@@ -642,6 +652,7 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
 #define BTF_CFG4 32, 1, 8, 10, 16
 #define BTF_CFG5 128, 8, 1, 6, 32
 #define BTF_CFG4U 32, 1, 8, 9, 16      // K == 32 with the unified tile list (overlapped kernel)
+#define BTF_CFG4H 64, 2, 4, 9, 32       // K == 32, two column parts per row tile (count weights)
 #define BTF_CFG3A 128, 8, 1, 19, 32    // K == 16 alternative: 8x1 warps, every warp owns all 19 tiles (no idle slot)
 
 static int cfg_wc(int cfg) { return (cfg == 1 || cfg == 4) ? 8 : (cfg == 3 ? 2 : 1); }
@@ -716,6 +727,35 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
         size_t so = p->cfg == 3 ? SMEM_OVL(BTF_CFG3) : (p->cfg == 4 ? SMEM_OVL(BTF_CFG4U) : SMEM_OVL(BTF_CFG5));
 #undef SMEM_OVL
         if (so <= 220 * 1024) { p->overlap = 1; p->smem_bytes = so; }
+        static const bool no_halves = getenv("BTF_STATS_NO_HALVES") != nullptr;
+        if (p->cfg == 4 && !weights_f64 && !no_halves && mdim_pad % 64 == 0 && kdim_pad % 32 == 0) {
+            int zwh = 4 * 9 * 8;
+            while (!((zwh % 16) == 4 || (zwh % 16) == 12)) ++zwh;
+            size_t sh = trans ? stats_smem_ovl<BTF_CFG4H, true, uint8_t>(K, zwh) : stats_smem_ovl<BTF_CFG4H, false, uint8_t>(K, zwh);
+            if (sh <= 222 * 1024) {
+                p->overlap = 2; p->smem_bytes = sh; p->zw = zwh;
+                p->BM = 64; p->KC = 32;
+                p->mtiles = mdim_pad / p->BM;
+                p->nchunks = kdim_pad / p->KC;
+                int ns = nsplit_request;
+                if (ns <= 0) {
+                    ns = 1;
+                    double best = -1.0;
+                    int maxs = p->nchunks < 64 ? p->nchunks : 64;
+                    for (int s = 1; s <= maxs; ++s) {
+                        long long ctas = (long long)p->mtiles * s * 2;
+                        long long waves = (ctas + sm_count - 1) / sm_count;
+                        double eff = (double)ctas / (double)(waves * sm_count);
+                        if (eff > best + 0.03) { best = eff; ns = s; }
+                        if (best > 0.97) break;
+                    }
+                }
+                if (ns > p->nchunks) ns = p->nchunks;
+                if (ns < 1) ns = 1;
+                p->chunks_per_split = (p->nchunks + ns - 1) / ns;
+                p->nsplit = (p->nchunks + p->chunks_per_split - 1) / p->chunks_per_split;
+            }
+        }
     }
     return p->smem_bytes <= 220 * 1024;
 }
@@ -732,16 +772,22 @@ void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* 
             else launch_stats_t<__VA_ARGS__, false, uint8_t, KF>(p, wt, sv, F, ld, m_valid, out, st);            \
         }                                                                                                        \
     } while (0)
-#define DISPATCH_OVL(KF, UNI_, ...)                                                                                        \
-    do {                                                                                                                   \
-        if (trans) {                                                                                                       \
-            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, true, double, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);  \
-            else launch_stats_ovl_t<__VA_ARGS__, true, uint8_t, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);             \
-        } else {                                                                                                           \
-            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, false, double, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st); \
-            else launch_stats_ovl_t<__VA_ARGS__, false, uint8_t, KF, UNI_>(p, wt, sv, F, ld, m_valid, out, st);            \
-        }                                                                                                                  \
+#define DISPATCH_OVL(KF, UNI_, ...)                                                                                           \
+    do {                                                                                                                      \
+        if (trans) {                                                                                                          \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, true, double, KF, UNI_, 1>(p, wt, sv, F, ld, m_valid, out, st);  \
+            else launch_stats_ovl_t<__VA_ARGS__, true, uint8_t, KF, UNI_, 1>(p, wt, sv, F, ld, m_valid, out, st);             \
+        } else {                                                                                                              \
+            if (weights_f64) launch_stats_ovl_t<__VA_ARGS__, false, double, KF, UNI_, 1>(p, wt, sv, F, ld, m_valid, out, st); \
+            else launch_stats_ovl_t<__VA_ARGS__, false, uint8_t, KF, UNI_, 1>(p, wt, sv, F, ld, m_valid, out, st);            \
+        }                                                                                                                     \
     } while (0)
+    if (p.overlap == 2) {
+        // K = 32, count weights: two column parts per row tile (64 rows, KC 32)
+        if (trans) launch_stats_ovl_t<BTF_CFG4H, true, uint8_t, 32, true, 2>(p, wt, sv, F, ld, m_valid, out, st);
+        else launch_stats_ovl_t<BTF_CFG4H, false, uint8_t, 32, true, 2>(p, wt, sv, F, ld, m_valid, out, st);
+        return;
+    }
     if (p.overlap) {
         // K = 16: measured on B200 (C2): rows 2.85 ms with the 8x1 layout vs 2.92 ms with 4x2,
         // columns 2.94 ms vs 2.89 ms -> 8x1 for the row contraction, 4x2 for the column contraction
