@@ -67,6 +67,7 @@ struct btf_engine {
     // statistics
     StatsPlan plan_row, plan_col;
     double *row_stats = nullptr, *col_stats = nullptr;
+    double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
     // workspaces
     double *work_L = nullptr, *work_y = nullptr, *partials = nullptr, *lam_partials = nullptr, *resid_partials = nullptr;
     size_t partials_n = 0;
@@ -263,6 +264,11 @@ int btf_create(const btf_config* c, btf_engine** out) {
         { delete e; return set_err(BTF_EINVAL, "no column-statistics plan for K=%d", c->nembeds); }
     CK(dev_alloc(&e->row_stats, e->plan_row.nsplit * e->plan_row.out_elems_per_split));
     CK(dev_alloc(&e->col_stats, e->plan_col.nsplit * e->plan_col.out_elems_per_split));
+    {
+        size_t zr = e->plan_row.zpre ? (size_t)e->Ppad * e->plan_row.zwg : 0;
+        size_t zc = e->plan_col.zpre ? (size_t)e->nloc_pad * e->plan_col.zwg : 0;
+        if (std::max(zr, zc)) CK(dev_alloc(&e->zbuf, std::max(zr, zc)));
+    }
 
     // workspaces (the blocked band solver works on K padded to 8 / 16 / 32)
     e->Kp = e->K <= 8 ? 8 : (e->K <= 16 ? 16 : 32);
@@ -297,7 +303,7 @@ void btf_destroy(btf_engine* e) {
     if (e->shard) nccl_shard_destroy(e->shard);
     void* ptrs[] = {e->W, e->V, e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c, e->scal, e->cnt, e->S, e->ntr, e->omega,
                     e->Yraw, e->Rdisp, e->nb_work, e->nb_hist, e->d_start, e->d_width, e->d_coef, e->pm_ptr, e->pm_row, e->pm_coef,
-                    e->row_stats, e->col_stats, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
+                    e->row_stats, e->col_stats, e->zbuf, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
@@ -716,8 +722,8 @@ static int enqueue_sweep(btf_engine* e) {
     phase_mark(e, PH_ROW_STATS);
     const void* wt = gauss ? (const void*)e->cnt : (const void*)e->omega;
     if ((mask & BTF_SAMPLE_W) && e->nloc > 0) {
-        launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->nloc, e->row_stats, st);
-        e->launches++;
+        launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->Ppad, e->nloc, e->row_stats, e->zbuf, st);
+        e->launches += e->plan_row.zpre ? 2 : 1;
         phase_mark(e, PH_ROW_SOLVE);
         RowSolveArgs ra;
         ra.stats = e->row_stats; ra.nsplit = e->plan_row.nsplit; ra.split_stride = e->plan_row.out_elems_per_split;
@@ -739,8 +745,9 @@ static int enqueue_sweep(btf_engine* e) {
     }
     // ---- V | rest
     if (mask & BTF_SAMPLE_V) {
-        launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->Ppad, e->P, e->col_stats, st);
-        e->launches++;
+        launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->nloc_pad, e->Ppad, e->P,
+                     e->col_stats, e->zbuf, st);
+        e->launches += e->plan_col.zpre ? 2 : 1;
         int nsplit = e->plan_col.nsplit;
         if (e->shard) {
             // sum the split partials locally is folded into the band kernel only on one GPU; across GPUs the

@@ -23,7 +23,8 @@ struct StatsPlan {
     int K, L, nct_z, nct_f, zw;
     int BM, KC;
     int mtiles, nchunks, nsplit, chunks_per_split;
-    int overlap;      // 1: Z generation overlapped with the DMMA loop (compile-time-K kernels)
+    int overlap;      // 1: Z generation overlapped with the DMMA loop (compile-time-K kernels), 2: + column parts
+    int zpre, zwg;    // 1: right operand pre-generated in global memory with row pitch zwg (stats_zpre.cu)
     size_t smem_bytes;
     size_t out_elems_per_split;   // m_valid * (L+K)
 };
@@ -32,8 +33,14 @@ struct StatsPlan {
 // weights_f64: weight operand is double (omega) instead of uint8 counts.
 bool plan_stats(StatsPlan* plan, int K, bool trans, bool weights_f64, int mdim_pad, int kdim_pad,
                 int m_valid, int nsplit_request, int sm_count);
+// frows: rows of F the contraction runs over (padded); zscratch: frows * plan.zwg doubles when plan.zpre
 void launch_stats(const StatsPlan& plan, bool trans, bool weights_f64, const void* wt, const double* sv,
-                  const double* F, long long ld, int m_valid, double* out, cudaStream_t st);
+                  const double* F, long long frows, long long ld, int m_valid, double* out, double* zscratch,
+                  cudaStream_t st);
+bool plan_stats_zpre(StatsPlan* p, bool trans, bool weights_f64, int mdim_pad, int kdim_pad, int nsplit_request,
+                     int sm_count);
+void launch_stats_zpre(const StatsPlan& p, bool trans, const void* wt, const double* sv, const double* F,
+                       long long frows, long long ld, int m_valid, double* out, double* Zg, cudaStream_t st);
 
 // ---------------------------------------------------------------- residual (nu2)
 // resid_partials[b] = sum over the block's cells of cnt*Mu^2 - 2*Mu*S

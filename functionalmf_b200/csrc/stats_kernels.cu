@@ -15,27 +15,12 @@
 // two-stage shared-memory ring; Z tiles are generated on chip from the small
 // factor tile; products run as mma.sync.m8n8k4.f64 (DMMA) -- tcgen05 has no FP64
 // kind, so this is the B200 FP64 tensor path.
-#include "kernels.h"
+#include "stats_common.cuh"
 #include <stdio.h>
 #include <algorithm>
 #include <stdlib.h>
 
 namespace btf {
-
-// ------------------------------------------------------------------ helpers
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 
 // ------------------------------------------------------------------ K0
 __global__ void prereduce_gaussian_kernel(const double* __restrict__ Y, int rows, int P, int R,
@@ -110,33 +95,6 @@ void launch_reduce_add(const double* src, int n, int stride, double* dst, cudaSt
 }
 
 // ------------------------------------------------------------------ K1
-struct StatsKArgs {
-    const void* wt;
-    const double* sv;
-    const double* F;
-    double* out;
-    long long ld;
-    int K, L, nct_z, nct_f, zw;
-    int nchunks, chunks_per_split;
-    int m_valid;
-    long long out_split_stride;
-};
-
-template <bool TRANS, typename WT, int BM, int KC>
-struct TileGeom {
-    // Shared-memory row strides (elements).  A 64-bit LDS is served per half-warp, so
-    // the four k-rows (or four m-rows) a half-warp touches must fall into disjoint
-    // 8-word bank groups: double strides are = 4 (mod 16); byte tiles use strides whose
-    // word offsets are distinct.  Every cp.async destination stays 16-byte aligned.
-    static constexpr int WROWS = TRANS ? KC : BM;
-    static constexpr int WSTR = sizeof(WT) == 1 ? (TRANS ? BM + 16 : 48) : (TRANS ? BM + 4 : KC + 4);
-    static constexpr int SSTR = TRANS ? BM + 4 : KC + 4;
-    static constexpr int WBYTES = WROWS * WSTR * (int)sizeof(WT);
-    static constexpr int SBYTES = WROWS * SSTR * 8;
-};
-
-__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
-
 // Column tiles (8 generated columns each): nct_z tiles of packed products, then nct_f
 // tiles of plain factor columns.  Warp column-group wc owns product tiles
 // [wc*ZPW, (wc+1)*ZPW) and factor tiles [wc*FPW, (wc+1)*FPW).  With KFIX > 0 all of this
@@ -757,11 +715,15 @@ bool plan_stats(StatsPlan* p, int K, bool trans, bool weights_f64, int mdim_pad,
             }
         }
     }
-    return p->smem_bytes <= 220 * 1024;
+    p->zpre = 0; p->zwg = 0;
+    if (plan_stats_zpre(p, trans, weights_f64, mdim_pad, kdim_pad, nsplit_request, sm_count)) return true;
+    return p->smem_bytes <= 226 * 1024;
 }
 
 void launch_stats(const StatsPlan& p, bool trans, bool weights_f64, const void* wt, const double* sv,
-                  const double* F, long long ld, int m_valid, double* out, cudaStream_t st) {
+                  const double* F, long long frows, long long ld, int m_valid, double* out, double* zscratch,
+                  cudaStream_t st) {
+    if (p.zpre && zscratch) { launch_stats_zpre(p, trans, wt, sv, F, frows, ld, m_valid, out, zscratch, st); return; }
 #define DISPATCH(KF, ...)                                                                                        \
     do {                                                                                                         \
         if (trans) {                                                                                             \
