@@ -278,7 +278,7 @@ int btf_create(const btf_config* c, btf_engine** out) {
     CK(dev_alloc(&e->work_y, (size_t)std::max(e->Mloc, 1) * e->wy_stride));
     e->partials_n = std::max<size_t>((size_t)(e->Ppad / 256) * (e->nloc_pad / 64), (size_t)2 * 148 * 16) + 64;
     CK(dev_alloc(&e->partials, e->partials_n));
-    CK(dev_alloc(&e->lam_partials, e->M));
+    CK(dev_alloc(&e->lam_partials, e->M + 512));     // [M] lam2 partials + scratch for the W sum of squares
     CK(dev_alloc(&e->resid_partials, e->M));
     CK(dev_alloc(&e->snapW, (size_t)e->N * e->K));
     CK(dev_alloc(&e->snapV, (size_t)e->P * e->K));
@@ -693,11 +693,11 @@ static int enqueue_sweep(btf_engine* e) {
     }
     phase_mark(e, PH_SIGMA2);
     if (mask & BTF_SAMPLE_SIGMA2) {
-        launch_w_sumsq(e->W, e->N, e->K, e->scal, st);
+        launch_w_sumsq(e->W, e->N, e->K, e->scal, e->lam_partials + e->M, st);
         ScalarStepArgs sa{e->scal, c.seed, c.sigma2_a, c.sigma2_b, inj(e, "g_sigma2")};
         const double nfree = e->N >= e->K ? (double)e->L + (double)(e->N - e->K) * e->K : 0.5 * e->N * (e->N + 1.0);
         launch_sigma2(sa, nfree, st);
-        e->launches += 2;
+        e->launches += 3;
     }
     phase_mark(e, PH_TAU2);
     HyperArgs ha;

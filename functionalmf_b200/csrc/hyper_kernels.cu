@@ -7,41 +7,44 @@
 
 namespace btf {
 
-// One thread per (column j, penalty row r): delta = Delta[r,:] . V[j,:,k] through the
-// (<= p+2)-point stencil, then the four-level inverse-gamma chain.
-__global__ void tau2_kernel(HyperArgs a) {
-    const int ncol = a.col_end - a.col_begin;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ncol * a.RD) return;
-    const int j = a.col_begin + e / a.RD, r = e % a.RD;
-    const int K = a.K;
+// One block per column j: V[j] (T x K) is staged in shared memory (coalesced), then one thread
+// per penalty row r evaluates delta = Delta[r,:] . V[j,:,k] through the (<= p+2)-point stencil
+// and runs the four-level inverse-gamma chain.
+__global__ void __launch_bounds__(128) tau2_kernel(HyperArgs a) {
+    extern __shared__ double vs[];            // [T][K]
+    const int j = a.col_begin + blockIdx.x;
+    const int K = a.K, T = a.T;
+    const double* Vj = a.V + (size_t)j * T * K;
+    for (int e = threadIdx.x; e < T * K; e += blockDim.x) vs[e] = Vj[e];
+    __syncthreads();
     const double lo = a.stability, hi = 1.0 / a.stability;
-    const int s0 = a.d_start[r], w = a.d_width[r];
-    const double* coef = a.d_coef + (size_t)r * a.d_maxw;
-    const double* Vj = a.V + ((size_t)j * a.T + s0) * K;
-    double ssq = 0.0;
-    for (int k = 0; k < K; ++k) {
-        double d = 0.0;
-        for (int x = 0; x < w; ++x) d += coef[x] * Vj[(size_t)x * K + k];
-        ssq += d * d;
-    }
-    const size_t o = (size_t)j * a.RD + r;
-    double g0, g1, g2, g3;
-    if (a.g_inject) {
-        const double* g = a.g_inject + (size_t)j * 4 * a.RD + r;
-        g0 = g[0]; g1 = g[a.RD]; g2 = g[2 * a.RD]; g3 = g[3 * a.RD];
-    } else {
-        Rng rng(a.seed, STREAM_TAU, a.scal->sweep, (uint64_t)o);
-        g0 = rng.gamma(0.5 * (K + 1));
-        g1 = rng.exponential(); g2 = rng.exponential(); g3 = rng.exponential();
-    }
     const double lam2 = a.scal->lam2;
-    double rate = ssq / (2.0 * lam2) + 1.0 / clampd(a.Tau2_c[o], lo, hi);
-    double tau2 = 1.0 / (g0 * (1.0 / clampd(rate, lo, hi)));
-    double c = 1.0 / (g1 * (1.0 / clampd(1.0 / tau2 + 1.0 / a.Tau2_b[o], lo, hi)));
-    double b = 1.0 / (g2 * (1.0 / clampd(1.0 / c + 1.0 / a.Tau2_a[o], lo, hi)));
-    double aa = 1.0 / (g3 * (1.0 / clampd(1.0 / b + 1.0, lo, hi)));
-    a.Tau2[o] = tau2; a.Tau2_c[o] = c; a.Tau2_b[o] = b; a.Tau2_a[o] = aa;
+    for (int r = threadIdx.x; r < a.RD; r += blockDim.x) {
+        const int s0 = a.d_start[r], w = a.d_width[r];
+        const double* coef = a.d_coef + (size_t)r * a.d_maxw;
+        double ssq = 0.0;
+        for (int k = 0; k < K; ++k) {
+            double d = 0.0;
+            for (int x = 0; x < w; ++x) d += coef[x] * vs[(s0 + x) * K + k];
+            ssq += d * d;
+        }
+        const size_t o = (size_t)j * a.RD + r;
+        double g0, g1, g2, g3;
+        if (a.g_inject) {
+            const double* g = a.g_inject + (size_t)j * 4 * a.RD + r;
+            g0 = g[0]; g1 = g[a.RD]; g2 = g[2 * a.RD]; g3 = g[3 * a.RD];
+        } else {
+            Rng rng(a.seed, STREAM_TAU, a.scal->sweep, (uint64_t)o);
+            g0 = rng.gamma(0.5 * (K + 1));
+            g1 = rng.exponential(); g2 = rng.exponential(); g3 = rng.exponential();
+        }
+        double rate = ssq / (2.0 * lam2) + 1.0 / clampd(a.Tau2_c[o], lo, hi);
+        double tau2 = 1.0 / (g0 * (1.0 / clampd(rate, lo, hi)));
+        double c = 1.0 / (g1 * (1.0 / clampd(1.0 / tau2 + 1.0 / a.Tau2_b[o], lo, hi)));
+        double b = 1.0 / (g2 * (1.0 / clampd(1.0 / c + 1.0 / a.Tau2_a[o], lo, hi)));
+        double aa = 1.0 / (g3 * (1.0 / clampd(1.0 / b + 1.0, lo, hi)));
+        a.Tau2[o] = tau2; a.Tau2_c[o] = c; a.Tau2_b[o] = b; a.Tau2_a[o] = aa;
+    }
 }
 
 // lam_partials[j] = 0.5 * sum_r ssq(j,r) / tau2[j,r]   (recomputed from the current Tau2;
@@ -71,8 +74,13 @@ void launch_tau2(const HyperArgs& a, cudaStream_t st) {
     const int ncol = a.col_end - a.col_begin;
     if (ncol <= 0) return;
     if (a.Tau2_a) {   // Tau2_a == nullptr: only the lam2 partials are wanted (Tau2 held fixed)
-        int total = ncol * a.RD;
-        tau2_kernel<<<(total + 127) / 128, 128, 0, st>>>(a);
+        size_t smem = (size_t)a.T * a.K * sizeof(double);
+        static size_t max_set = 0;
+        if (smem > 48 * 1024 && smem > max_set) {
+            cudaFuncSetAttribute(tau2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            max_set = smem;
+        }
+        tau2_kernel<<<ncol, 128, smem, st>>>(a);
     }
     if (a.lam_partials) lam_partial_kernel<<<ncol, 128, 0, st>>>(a);
 }
@@ -131,20 +139,33 @@ void launch_lam2(const ScalarStepArgs& a, const double* lam_partials, int M, int
     lam2_kernel<<<1, 256, 0, st>>>(a, lam_partials, M, ref_compat, shape);
 }
 
-// sum of squares of the free (lower-triangular) entries of W (factor.py:155-174)
-__global__ void w_sumsq_kernel(const double* __restrict__ W, int N, int K, Scalars* scal) {
+// sum of squares of the free (lower-triangular) entries of W (factor.py:155-174): per-block
+// partials, combined in a fixed order by w_sumsq_final_kernel (deterministic)
+__global__ void __launch_bounds__(256) w_sumsq_kernel(const double* __restrict__ W, int N, int K, double* partials) {
     __shared__ double sh[32];
     double v = 0.0;
     const long long total = (long long)N * K;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int i = (int)(e / K), k = (int)(e - (long long)i * K);
         if (k <= i) { double w = W[e]; v += w * w; }
     }
     v = block_sum(v, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+__global__ void w_sumsq_final_kernel(const double* partials, int n, Scalars* scal) {
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    v = block_sum(v, sh);
     if (threadIdx.x == 0) scal->w_sumsq = v;
 }
-void launch_w_sumsq(const double* W, int N, int K, Scalars* scal, cudaStream_t st) {
-    w_sumsq_kernel<<<1, 1024, 0, st>>>(W, N, K, scal);
+void launch_w_sumsq(const double* W, int N, int K, Scalars* scal, double* partials, cudaStream_t st) {
+    long long total = (long long)N * K;
+    int nb = (int)((total + 2047) / 2048);
+    if (nb > 296) nb = 296;
+    if (nb < 1) nb = 1;
+    w_sumsq_kernel<<<nb, 256, 0, st>>>(W, N, K, partials);
+    w_sumsq_final_kernel<<<1, 256, 0, st>>>(partials, nb, scal);
 }
 
 __global__ void bump_sweep_kernel(Scalars* s) { s->sweep += 1ull; }

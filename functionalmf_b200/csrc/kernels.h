@@ -110,7 +110,7 @@ void launch_sigma2(const ScalarStepArgs& a, double n_free, cudaStream_t st);
 // lam2, lam2_a | rest
 void launch_lam2(const ScalarStepArgs& a, const double* lam_partials, int M, int ref_compat, double shape,
                  cudaStream_t st);
-void launch_w_sumsq(const double* W, int N, int K, Scalars* scal, cudaStream_t st);
+void launch_w_sumsq(const double* W, int N, int K, Scalars* scal, double* partials /* >= 296 */, cudaStream_t st);
 void launch_bump_sweep(Scalars* scal, cudaStream_t st);
 void launch_clear_info(Scalars* scal, cudaStream_t st);
 void launch_set_resid(Scalars* scal, const double* partials, int n, cudaStream_t st);   // resid = ss_total + sum

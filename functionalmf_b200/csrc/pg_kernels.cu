@@ -22,7 +22,7 @@ __device__ __forceinline__ double log_phi(double x) {
     return log(0.5 * erfcx(u)) - u * u;
 }
 
-struct PgTilt { double Z, fz, pmass; };
+struct PgTilt { double Z, fz, pmass, inv_fz, inv_p, inv_q; };   // + reciprocals reused by every draw of the cell
 
 __device__ __forceinline__ PgTilt pg_setup(double z) {
     PgTilt c;
@@ -41,6 +41,9 @@ __device__ __forceinline__ PgTilt pg_setup(double z) {
         qdivp = 4.0 / PG_PI * (exp(x0 - c.Z + log_phi(b)) + exp(x0 + c.Z + log_phi(a)));
     }
     c.pmass = 1.0 / (1.0 + qdivp);
+    c.inv_fz = 1.0 / c.fz;
+    c.inv_p = 1.0 + qdivp;                               // 1 / pmass
+    c.inv_q = c.pmass < 1.0 ? 1.0 / (1.0 - c.pmass) : 0.0;
     return c;
 }
 
@@ -103,8 +106,8 @@ __device__ double pg_one(Rng& rng, const PgTilt& c) {
         const uint4 r = rng.next4();
         const double u1 = Rng::to_unit(r.x, r.y), u2 = Rng::to_unit(r.z, r.w);
         double X;
-        if (u1 < c.pmass) X = PG_TRUNC - log(u1 / c.pmass) / c.fz;       // u1 / pmass is U(0,1) given the branch
-        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) / (1.0 - c.pmass));
+        if (u1 < c.pmass) X = PG_TRUNC - log(u1 * c.inv_p) * c.inv_fz;    // u1 / pmass is U(0,1) given the branch
+        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) * c.inv_q);
         const double arg = X > PG_TRUNC ? -PG_PI * PG_PI * X : -4.0 / X;
         // u2 <= 1 - 3 exp(arg): FP32 screen (the threshold is within 2e-2 of 1), FP64 when borderline
         const float thr = 1.0f - 3.0f * __expf((float)arg);
