@@ -214,6 +214,33 @@ def cpu_baseline(cfg, budget_s=20.0, seed=2):
             'sweep_seconds_est': sweep_s, 'prereduce_seconds_sample': t_pre}
 
 
+def bind_to_gpu_numa_node(device):
+    """Best effort: run this process on the CPUs local to the GPU's PCIe root so that the pinned
+    host buffers (first-touch) live on the near NUMA node -- the H2D copy of Y runs at ~51 GB/s
+    from the near node and ~18 GB/s from the far one on these hosts."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device)
+        bus = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/local_cpulist' % bus) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- our arm
 def bench_ours(args):
     import torch
@@ -232,6 +259,8 @@ def bench_ours(args):
     if world != args.gpus:
         raise SystemExit('--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run' % (args.gpus, world))
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     N, M, T, R, K, order = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K'], cfg['order']
@@ -290,10 +319,12 @@ def bench_ours(args):
         assert np.all(np.isfinite(res_S)) and np.all(np.isfinite(res_V[-1]))
         d2h = (res_W[0].nbytes + res_V[0].nbytes + res_T[0].nbytes + res_S[0].nbytes)
         e2e = {'value': K_e2e / e2e_s, 'unit': 'sweeps/s', 'h2d_bytes_per_step': Y.nbytes / float(K_e2e),
-               'd2h_bytes_per_step': d2h, 'seconds': e2e_s, 'upload_seconds': t_up,
+               'd2h_bytes_per_step': d2h, 'seconds': e2e_s, 'upload_seconds': t_up, 'cpu_affinity': numa,
                'host_buffers': sorted(set(how for _, how in __import__('functionalmf_b200.engine', fromlist=['x']).PINNED_LOG)),
                'includes': 'H2D of Y (%.2f GB per rank, once) + pre-reduction, %d sweeps, D2H of W,V,Tau2,scalars '
                            'every sweep' % (Y.nbytes / 1e9, K_e2e)}
+
+    os.sched_setaffinity(0, affinity0)        # the CPU baseline below uses every host core again
 
     # ---------------- device-resident leg (data already in HBM from the e2e leg)
     for _ in range(max(3, args.warmup)):

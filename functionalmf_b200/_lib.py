@@ -73,6 +73,8 @@ SIGNATURES = {
     'btf_run_segment': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P]),
     'btf_synchronize': (C.c_int, [_P]),
     'btf_init_state': (C.c_int, [_P, C.c_int32]),
+    'btf_mu_stats_track': (C.c_int, [_P, C.c_int32]),
+    'btf_mu_stats_get': (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),
     'btf_host_alloc': (_P, [C.c_size_t]),
     'btf_host_free': (None, [_P]),
     'btf_host_register': (C.c_int, [_P, C.c_size_t]),

@@ -67,6 +67,7 @@ struct btf_engine {
     // statistics
     StatsPlan plan_row, plan_col;
     double *row_stats = nullptr, *col_stats = nullptr;
+    double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
     // workspaces
     double *work_L = nullptr, *work_y = nullptr, *partials = nullptr, *lam_partials = nullptr, *resid_partials = nullptr;
@@ -303,7 +304,7 @@ void btf_destroy(btf_engine* e) {
     if (e->shard) nccl_shard_destroy(e->shard);
     void* ptrs[] = {e->W, e->V, e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c, e->scal, e->cnt, e->S, e->ntr, e->omega,
                     e->Yraw, e->Rdisp, e->nb_work, e->nb_hist, e->d_start, e->d_width, e->d_coef, e->pm_ptr, e->pm_row, e->pm_coef,
-                    e->row_stats, e->col_stats, e->zbuf, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
+                    e->row_stats, e->col_stats, e->zbuf, e->mu_mean, e->mu_m2, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
@@ -934,6 +935,12 @@ int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t 
         if (rc) return rc;
         if (step >= first_save && (step - first_save) % nthin == 0) {
             const size_t sidx = (size_t)sample_offset + (size_t)(step - first_save) / nthin;
+            if (e->mu_track) {
+                e->mu_count += 1;
+                launch_mu_moments(e->W + (size_t)e->cfg.row_begin * e->K, e->V, e->K, e->nloc, e->P, e->mu_mean, e->mu_m2,
+                                  (double)e->mu_count, e->stream);
+                e->launches++;
+            }
             // snapshot on the compute stream (device-to-device), drain on the copy stream
             if (pending) CK(cudaStreamWaitEvent(e->stream, e->ev_copied, 0));
             if (W_out) CK(cudaMemcpyAsync(e->snapW, e->W, wn * 8, cudaMemcpyDeviceToDevice, e->stream));
@@ -966,6 +973,39 @@ int btf_run(btf_engine* e, int32_t nburn, int32_t nthin, int32_t nsamples, doubl
     if (nburn < 0 || nthin < 1 || nsamples < 0) return set_err(BTF_EINVAL, "bad chain lengths");
     return btf_run_segment(e, nburn + nthin * nsamples, nburn, nthin, 0, W_out, V_out, Tau2_out, scalars_out, R_out,
                            omega_out);
+}
+
+// Running posterior moments of Mu = einsum('nk,mtk->nmt', W, V) (genlasso.py:51-65 keeps every
+// sample on the host instead): track != 0 (re)starts the accumulation, every sample saved by
+// btf_run / btf_run_segment then updates mean and M2 on the device.
+int btf_mu_stats_track(btf_engine* e, int32_t track) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    const size_t n = (size_t)e->nloc * e->P;
+    if (track) {
+        if (!e->mu_mean) { CK(dev_alloc(&e->mu_mean, n)); CK(dev_alloc(&e->mu_m2, n)); }
+        else { CK(cudaMemset(e->mu_mean, 0, n * 8)); CK(cudaMemset(e->mu_m2, 0, n * 8)); }
+        e->mu_count = 0;
+    }
+    e->mu_track = track != 0;
+    return BTF_OK;
+}
+// mean_out, var_out: [nloc, M, T] (either may be NULL); variance with the 1/(count-1) normalisation
+int btf_mu_stats_get(btf_engine* e, double* mean_out, double* var_out, int64_t* count_out) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    if (!e->mu_mean) return set_err(BTF_ESTATE, "posterior moments are not being tracked");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    const size_t n = (size_t)e->nloc * e->P;
+    if (count_out) *count_out = e->mu_count;
+    if (mean_out) CK(cudaMemcpy(mean_out, e->mu_mean, n * 8, cudaMemcpyDeviceToHost));
+    if (var_out) {
+        CK(cudaMemcpy(var_out, e->mu_m2, n * 8, cudaMemcpyDeviceToHost));
+        const double sc = e->mu_count > 1 ? 1.0 / (double)(e->mu_count - 1) : 0.0;
+        for (size_t i = 0; i < n; ++i) var_out[i] *= sc;
+    }
+    return BTF_OK;
 }
 
 // pinned host buffers for the result arrays (async device-to-host copies need them)

@@ -47,6 +47,10 @@ void launch_stats_zpre(const StatsPlan& p, bool trans, const void* wt, const dou
 void launch_residual(const uint8_t* cnt, const double* S, long long ld, const double* W, const double* V,
                      int nrows_pad, int Ppad, int K, double* partials, int* nblocks_out, cudaStream_t st);
 
+// running posterior mean / M2 of Mu = W V^T over the local cells (Welford), count = samples so far
+void launch_mu_moments(const double* W, const double* V, int K, int nloc, int P, double* mean, double* m2,
+                       double count, cudaStream_t st);
+
 // ---------------------------------------------------------------- K2 row solve
 struct RowSolveArgs {
     const double* stats;   // [nsplit][nloc][L+K]

@@ -813,4 +813,47 @@ void launch_residual(const uint8_t* cnt, const double* S, long long ld, const do
     *nblocks_out = grid.x * grid.y;
 }
 
+
+// ------------------------------------------------------------------ running posterior moments of Mu
+// Welford update of mean and M2 of Mu[i,p] = w_i . v_p for every local cell, one pass per saved
+// sample (at C2 a thousand saved (W, V) samples are 10 GB, the two moment
+// tensors 4.3 GB).  Same tiling as the residual pass: 64 rows x 256 cells per block.
+template <int KMAX>
+__global__ void __launch_bounds__(256) mu_moments_kernel(const double* __restrict__ W, const double* __restrict__ V,
+                                                         int K, int nloc, int P, double* __restrict__ mean,
+                                                         double* __restrict__ m2, double count) {
+    __shared__ double ws[64 * KMAX];
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const int i0 = blockIdx.y * 64;
+    for (int e = threadIdx.x; e < 64 * K; e += 256) ws[e] = W[(long long)i0 * K + e];
+    double v[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) v[k] = (k < K && p < P) ? V[(long long)p * K + k] : 0.0;
+    __syncthreads();
+    if (p >= P) return;
+    const double inv = 1.0 / count;
+    for (int r = 0; r < 64; ++r) {
+        const int il = i0 + r;
+        if (il >= nloc) break;
+        double mu = 0.0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) mu += ws[r * K + k] * v[k];
+        const long long o = (long long)il * P + p;
+        const double m = mean[o];
+        const double d = mu - m;
+        const double mn = m + d * inv;
+        mean[o] = mn;
+        m2[o] += d * (mu - mn);
+    }
+}
+
+void launch_mu_moments(const double* W, const double* V, int K, int nloc, int P, double* mean, double* m2,
+                       double count, cudaStream_t st) {
+    dim3 grid((P + 255) / 256, (nloc + 63) / 64);
+    if (K <= 8) mu_moments_kernel<8><<<grid, 256, 0, st>>>(W, V, K, nloc, P, mean, m2, count);
+    else if (K <= 16) mu_moments_kernel<16><<<grid, 256, 0, st>>>(W, V, K, nloc, P, mean, m2, count);
+    else mu_moments_kernel<32><<<grid, 256, 0, st>>>(W, V, K, nloc, P, mean, m2, count);
+}
+
 }  // namespace btf

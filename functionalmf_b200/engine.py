@@ -160,6 +160,17 @@ class Engine(object):
         L.check(self.lib.btf_run_segment(self._h, int(nsweeps), int(first_save), int(nthin), int(sample_offset),
                                          _ptr(W), _ptr(V), _ptr(Tau2), _ptr(scalars), _ptr(R), _ptr(omega)))
 
+    def track_mu_stats(self, on=True):
+        L.check(self.lib.btf_mu_stats_track(self._h, 1 if on else 0))
+
+    def mu_stats(self):
+        """(mean, variance, count) of Mu over the samples saved since track_mu_stats(True)."""
+        shape = (self.nloc, self.M, self.T)
+        mean, var = np.empty(shape), np.empty(shape)
+        cnt = C.c_int64(0)
+        L.check(self.lib.btf_mu_stats_get(self._h, _ptr(mean), _ptr(var), C.byref(cnt)))
+        return mean, var, int(cnt.value)
+
     def synchronize(self):
         L.check(self.lib.btf_synchronize(self._h))
 

@@ -39,12 +39,17 @@ class _BayesianModel(object):
         return results
 
     def run_gibbs(self, data, nburn=1000, nthin=1, nsamples=1000, verbose=True, print_freq=100,
-                  callback=None, **kwargs):
-        '''Run a gibbs sampler on the model (genlasso.py:37-66).'''
+                  callback=None, track_mu=False, **kwargs):
+        '''Run a gibbs sampler on the model (genlasso.py:37-66).  ``track_mu=True`` (engine
+        extension) additionally returns ``results['Mu_mean']`` / ``results['Mu_var']``: the
+        posterior mean and variance of einsum('nk,mtk->nmt', W, V) over the saved samples,
+        accumulated on the device.'''
         nsteps = nburn + nthin * nsamples
         if callback is not None:
             return self._run_gibbs_callback(data, nburn, nthin, nsamples, verbose, print_freq, callback, **kwargs)
         self._begin(data)
+        if track_mu:
+            self._engine.track_mu_stats(True)
         results = self._alloc_results(nsamples)
         outs = self._result_buffers(results)
         seg = max(1, int(print_freq)) if verbose else nsteps
@@ -62,7 +67,11 @@ class _BayesianModel(object):
                 self._engine.sweep(stop - step)
             step = stop
         self._end()
-        return self._finish_results(results)
+        results = self._finish_results(results)
+        if track_mu:
+            results['Mu_mean'], results['Mu_var'], _ = self._engine.mu_stats()
+            self._engine.track_mu_stats(False)
+        return results
 
     def _run_gibbs_callback(self, data, nburn, nthin, nsamples, verbose, print_freq, callback, **kwargs):
         nsteps = nburn + nthin * nsamples

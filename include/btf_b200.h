@@ -110,6 +110,11 @@ int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t 
                     double* W_out, double* V_out, double* Tau2_out, double* scalars_out,
                     double* R_out, double* omega_out);
 int btf_synchronize(btf_engine* e);
+/* Running posterior mean / variance of Mu = einsum('nk,mtk->nmt', W, V) on the device, updated at
+ * every saved sample (the reference keeps all samples on the host,
+ * genlasso.py:51-65).  mean_out / var_out: [Nloc, M, T], either may be NULL. */
+int btf_mu_stats_track(btf_engine* e, int32_t track);
+int btf_mu_stats_get(btf_engine* e, double* mean_out, double* var_out, int64_t* count_out);
 /* Constructor draws from the priors on the device (factor.py:230-253, 293-304, 560-563;
  * utils.py:115-124).  init_mask bits: 1 sigma2, 2 lam2, 4 nu2, 8 Tau2, 16 W, 32 V, 64 R. */
 int btf_init_state(btf_engine* e, int32_t init_mask);

@@ -108,3 +108,20 @@ def test_binomial_and_negbin_classes_run():
     assert mn.R.shape == (N, 1, 1) and np.all(mn.R > 1)
     res = mn.run_gibbs(Yc, nburn=2, nthin=1, nsamples=3, verbose=False)
     assert res['R'].shape == (3, N, 1, 1) and np.all(res['R'] > 1) and np.all(np.isfinite(res['V']))
+
+
+def test_device_posterior_moments_match_saved_samples():
+    """the running mean / variance of Mu accumulated on the device equal the
+    moments computed on the host from the saved (W, V) samples."""
+    from functionalmf_b200 import GaussianBayesianTensorFiltering
+    rs = np.random.RandomState(6)
+    N, M, T, K = 70, 9, 11, 4
+    Y = rs.normal(size=(N, M, T, 2)) + rs.normal(size=(N, 1, 1, 1))
+    Y[rs.random_sample(Y.shape) < 0.15] = np.nan
+    model = GaussianBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=2, seed=9, sigma2_init=0.5, lam2_init=0.1,
+                                            nu2_init=1.0)
+    res = model.run_gibbs(Y, nburn=5, nthin=2, nsamples=40, verbose=False, track_mu=True)
+    Mu = np.einsum('znk,zmtk->znmt', res['W'], res['V'])
+    assert res['Mu_mean'].shape == (N, M, T)
+    assert np.allclose(res['Mu_mean'], Mu.mean(axis=0), rtol=1e-10, atol=1e-12)
+    assert np.allclose(res['Mu_var'], Mu.var(axis=0, ddof=1), rtol=1e-8, atol=1e-12)
