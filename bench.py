@@ -306,6 +306,11 @@ def bench_ours(args):
         # ------------ end-to-end leg: host buffers -> run_gibbs-style segment -> host samples
         res_W = pinned_empty((K_e2e, N, K)); res_V = pinned_empty((K_e2e, M, T, K))
         res_T = pinned_empty((K_e2e, M, RD)); res_S = pinned_empty((K_e2e, 4))
+        # untimed warm-up pass of the same path (CUDA module loading, graph instantiation, staging
+        # allocation), then the timed pass: upload + pre-reduction + K sweeps + per-sweep D2H
+        eng.set_data_gaussian(Y)
+        eng.run_segment(min(max(3, args.warmup), K_e2e), 0, 1, 0, W=res_W, V=res_V, Tau2=res_T, scalars=res_S)
+        eng.synchronize()
         barrier()
         l0 = eng.kernel_launches
         t0 = time.perf_counter()
@@ -361,9 +366,9 @@ def bench_ours(args):
         hbm_peak = hbm_peak or 6650.0
         bytes_stats = 2.0 * cells * 9.0 / world
         # DRAM traffic per launch of the dominant kernel from the ncu --set full capture of this
-        # workload (profiles/r1_ncu_stats_r1_final_summary.txt: rows 2.425 GB read + 0.027 GB written,
-        # columns 2.418 GB + 0.143 GB); algorithmic bytes per launch are cells * 9 B = 2.416 GB
-        traffic = 2.5063e9 if (args.workload == 'c2' and world == 1) else None
+        # workload (profiles/r1_ncu_stats_zpre_summary.txt: rows 2.504 GB read + 0.029 GB written,
+        # columns 2.436 GB + 0.144 GB); algorithmic bytes per launch are cells * 9 B = 2.416 GB
+        traffic = 2.5566e9 if (args.workload == 'c2' and world == 1) else None
         out = {
             'metric': 'Gibbs sweeps/sec', 'value': args.steps / (ms * 1e-3), 'unit': 'sweeps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
