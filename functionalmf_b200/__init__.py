@@ -6,7 +6,8 @@ behind the C ABI of ``include/btf_b200.h`` (``libbtf_b200.so``).
 """
 from .factor import (BayesianTensorFiltering, GaussianBayesianTensorFiltering,          # noqa: F401
                      BinomialBayesianTensorFiltering, NegativeBinomialBayesianTensorFiltering)
-from .constrained import ConstrainedNonconjugateBayesianTensorFiltering                  # noqa: F401
+from .constrained import (ConstrainedNonconjugateBayesianTensorFiltering,                # noqa: F401
+                          NonconjugateBayesianTensorFiltering)
 from ._lib import BTFError, BTFLibraryError, NotPositiveDefiniteError                    # noqa: F401
 from .utils import ilogit, mse, mae, bayes_grid_penalty                                  # noqa: F401
 

@@ -205,3 +205,51 @@ class ConstrainedNonconjugateBayesianTensorFiltering(BayesianTensorFiltering):
     def logprob(self, data, **kwargs):
         tau = (self.W[:, None, None] * self.V[None]).sum(axis=-1)
         return self.loglikelihood(data, tau, self.W, self.V)
+
+
+class NonconjugateBayesianTensorFiltering(ConstrainedNonconjugateBayesianTensorFiltering):
+    """factor.py:567-612: black-box likelihood ``loglikelihood(W, V, data)``, joint elliptical slice
+    sampling of all free W entries, then of all of V.  The prior draws the ellipse needs --
+    W ~ N(0, sigma2) on the free entries (factor.py:155-174) and one banded MVN draw per column
+    (factor.py:176-194, unclipped prior precision) -- come from the engine in one batched step each;
+    the slice sampling itself and the likelihood callback stay on the host as in the reference."""
+
+    def __init__(self, nrows, ncols, ndepth, loglikelihood, **kwargs):
+        no_constraints = np.zeros((0, ndepth + 1))
+        super().__init__(nrows, ncols, ndepth, loglikelihood, no_constraints, **kwargs)
+
+    def _likelihood_options(self):
+        return dict(clip_prior_precision=0)
+
+    def _free_mask(self):
+        m = np.ones((self.nrows, self.nembeds), dtype=bool)
+        d = min(self.nrows, self.nembeds)
+        iu = np.triu_indices(d, k=1, m=self.nembeds)
+        m[:d][iu] = False
+        return m
+
+    def _resample_W(self, data, z=None):
+        from .ess import elliptical_slice
+        self._engine_step(L.SAMPLE_W, 'z_W', z)
+        prior = self._engine.get('W')
+        free = self._free_mask()
+
+        def ll(vec, args):
+            W = np.zeros_like(self.W)
+            W[free] = vec
+            return self.loglikelihood(W, self.V, args)
+        new, _ = elliptical_slice(self.W[free], prior[free], ll, ll_args=data, rng=self._rng)
+        self.W[free] = new
+
+    def _resample_V(self, data, z=None):
+        from .ess import elliptical_slice
+        self._engine_step(L.SAMPLE_V, 'z_V', z)
+        prior = self._engine.get('V')
+
+        def ll(vec, args):
+            return self.loglikelihood(self.W, vec.reshape(self.V.shape), args)
+        new, _ = elliptical_slice(self.V.ravel(), prior.ravel(), ll, ll_args=data, rng=self._rng)
+        self.V[:] = new.reshape(self.V.shape)
+
+    def logprob(self, data, **kwargs):
+        return self.loglikelihood(self.W, self.V, data)

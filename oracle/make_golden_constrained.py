@@ -160,7 +160,45 @@ def make_gass_cases(seed=3):
     print('wrote', path)
 
 
+def make_ess_cases(seed=9):
+    """Direct calls of the reference's elliptical_slice_ (elliptical_slice.py:59-124)."""
+    from functionalmf.elliptical_slice import elliptical_slice_
+    rs = np.random.RandomState(seed)
+    out = {}
+    ncase = 10
+    orig = np.random.rand
+    for c in range(ncase):
+        d = 3 + c
+        x = rs.normal(size=d)
+        nu = rs.normal(size=d) * 1.5
+        target = rs.normal(size=d)
+        mu = rs.normal(size=d) * (c % 2)
+        tape = []
+
+        def rand(*a):
+            v = rs.random_sample()
+            tape.append(v)
+            return v
+
+        def ll(pts, args):
+            return -2.0 * ((pts - args) ** 2).sum()
+        np.random.rand = rand
+        try:
+            xn, lln = elliptical_slice_(x.copy(), nu, ll, ll_args=target, mu=mu)
+        finally:
+            np.random.rand = orig
+        pre = 'e%d_' % c
+        out[pre + 'x'], out[pre + 'nu'], out[pre + 'target'], out[pre + 'mu'] = x, nu, target, mu
+        out[pre + 'u'] = np.array(tape)
+        out[pre + 'xn'], out[pre + 'lln'] = xn, np.array([lln])
+    out['ncase'] = np.array([ncase])
+    path = os.path.join(ROOT, 'tests', 'golden', 'ess_cases.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path)
+
+
 if __name__ == '__main__':
+    make_ess_cases()
     make_gass_cases()
     make_model_case('constrained_plain', False, 41)
     make_model_case('constrained_ep', True, 42)

@@ -44,3 +44,28 @@ def test_feasible_angles_cover_whole_ellipse_when_unconstrained():
     a, b, c = np.array([1.0, 2.0]), np.array([0.1, -0.2]), np.array([-5.0, -9.0])
     g = feasible_angles(a, b, c, 17)
     assert len(g) == 17 and np.isclose(g[0], -np.pi) and np.isclose(g[-1], np.pi)
+
+
+def test_elliptical_slice_matches_reference_transitions():
+    """functionalmf_b200/ess.py against recorded calls of the reference's elliptical_slice_."""
+    from functionalmf_b200.ess import elliptical_slice
+    z = np.load(os.path.join(GOLDEN, 'ess_cases.npz'))
+
+    class Replay(object):
+        def __init__(self, u):
+            self.u = list(u)
+
+        def rand(self):
+            return self.u.pop(0)
+
+    for c in range(int(z['ncase'][0])):
+        pre = 'e%d_' % c
+        target = z[pre + 'target']
+
+        def ll(pts, args):
+            return -2.0 * ((pts - args) ** 2).sum()
+        rng = Replay(z[pre + 'u'])
+        xn, lln = elliptical_slice(z[pre + 'x'].copy(), z[pre + 'nu'], ll, ll_args=target, mu=z[pre + 'mu'], rng=rng)
+        assert not rng.u
+        assert np.allclose(xn, z[pre + 'xn'], rtol=1e-12, atol=1e-14), c
+        assert abs(lln - float(z[pre + 'lln'][0])) < 1e-10 * max(1.0, abs(lln))

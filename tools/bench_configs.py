@@ -53,6 +53,17 @@ def main():
         eng.set_data_gaussian(Y)
         run('C1 same, eager launches', eng, 2000)
         eng.close()
+        # the shipped example end to end through the drop-in class: 2000 sweeps, every post-burn-in
+        # sample copied back (examples/gaussian_tensor_filtering.py:49-51, 73)
+        from functionalmf_b200 import GaussianBayesianTensorFiltering
+        model = GaussianBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=2, sigma2_init=0.5, nthreads=1,
+                                                lam2_init=0.1, nu2_init=1, seed=1)
+        model.run_gibbs(Y, nburn=10, nthin=1, nsamples=10, verbose=False)
+        t0 = time.time()
+        res = model.run_gibbs(Y, nburn=1000, nthin=1, nsamples=1000, verbose=False)
+        dt = time.time() - t0
+        print(json.dumps(dict(config='C1 run_gibbs(nburn=1000, nthin=1, nsamples=1000) through the Python class',
+                              seconds=dt, sweeps_per_s=2000 / dt, samples=int(res['W'].shape[0]))), flush=True)
     if 'c4' in which:
         N, M, T, K = 19, 19, 228, 10
         W, V = truth(rs, N, M, T, K)
