@@ -22,6 +22,7 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -45,6 +46,7 @@ static bool load_api() {
     SYM(AllGather, "ncclAllGather")
     SYM(AllReduce, "ncclAllReduce")
     SYM(Reduce, "ncclReduce")
+    SYM(ReduceScatter, "ncclReduceScatter")
     SYM(Broadcast, "ncclBroadcast")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
@@ -66,6 +68,7 @@ struct NcclShard {
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0, N = 0, M = 0;
     std::vector<int> rb, re, cb, ce;   // per-rank [begin, end) of rows and columns
+    bool uniform_rows = false, uniform_cols = false;   // equal contiguous blocks: single collectives apply
     double* scratch = nullptr;
 };
 
@@ -108,6 +111,14 @@ NcclShard* nccl_shard_create(const char* id128, int world, int rank, int N, int 
         s->cb.push_back(all[4 * k + 2]); s->ce.push_back(all[4 * k + 3]);
     }
     cudaMalloc((void**)&s->scratch, 8 * sizeof(double));
+    auto uniform = [&](const std::vector<int>& b, const std::vector<int>& e) {
+        const int cnt = e[0] - b[0];
+        for (int k = 0; k < world; ++k)
+            if (e[k] - b[k] != cnt || b[k] != k * cnt) return false;
+        return cnt > 0;
+    };
+    s->uniform_rows = uniform(s->rb, s->re);
+    s->uniform_cols = uniform(s->cb, s->ce);
     return s;
 }
 
@@ -119,7 +130,12 @@ void nccl_shard_destroy(NcclShard* s) {
 }
 
 static int gather_blocks(NcclShard* s, double* base, const std::vector<int>& b, const std::vector<int>& e, size_t unit,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool uniform) {
+    if (uniform) {      // equal blocks: one in-place all-gather
+        const size_t cnt = (size_t)(e[0] - b[0]) * unit;
+        NC(g_api.AllGather(base + (size_t)b[s->rank] * unit, base, cnt, ncclFloat64, s->comm, st));
+        return 0;
+    }
     NC(g_api.GroupStart());
     for (int r = 0; r < s->world; ++r) {
         size_t cnt = (size_t)(e[r] - b[r]) * unit;
@@ -131,9 +147,9 @@ static int gather_blocks(NcclShard* s, double* base, const std::vector<int>& b, 
     return 0;
 }
 
-int nccl_allgather_rows(NcclShard* s, double* W, int K, cudaStream_t st) { return gather_blocks(s, W, s->rb, s->re, K, st); }
-int nccl_allgather_cols(NcclShard* s, double* V, int n, cudaStream_t st) { return gather_blocks(s, V, s->cb, s->ce, n, st); }
-int nccl_allgather_doubles(NcclShard* s, double* v, cudaStream_t st) { return gather_blocks(s, v, s->cb, s->ce, 1, st); }
+int nccl_allgather_rows(NcclShard* s, double* W, int K, cudaStream_t st) { return gather_blocks(s, W, s->rb, s->re, K, st, s->uniform_rows); }
+int nccl_allgather_cols(NcclShard* s, double* V, int n, cudaStream_t st) { return gather_blocks(s, V, s->cb, s->ce, n, st, s->uniform_cols); }
+int nccl_allgather_doubles(NcclShard* s, double* v, cudaStream_t st) { return gather_blocks(s, v, s->cb, s->ce, 1, st, s->uniform_cols); }
 
 __global__ void collapse_splits_kernel(double* x, int nsplit, size_t stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,6 +163,11 @@ __global__ void collapse_splits_kernel(double* x, int nsplit, size_t stride) {
 int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,
                           cudaStream_t st) {
     if (nsplit > 1) collapse_splits_kernel<<<148 * 8, 256, 0, st>>>(col_stats, nsplit, split_stride);
+    if (s->uniform_cols) {   // equal column blocks: one in-place reduce-scatter
+        const size_t cnt = (size_t)(s->ce[0] - s->cb[0]) * per_col_elems;
+        NC(g_api.ReduceScatter(col_stats, col_stats + (size_t)s->rank * cnt, cnt, ncclFloat64, ncclSum, s->comm, st));
+        return 0;
+    }
     NC(g_api.GroupStart());
     for (int r = 0; r < s->world; ++r) {
         size_t cnt = (size_t)(s->ce[r] - s->cb[r]) * per_col_elems;
