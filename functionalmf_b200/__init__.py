@@ -9,6 +9,8 @@ from .factor import (BayesianTensorFiltering, GaussianBayesianTensorFiltering,  
 from .constrained import (ConstrainedNonconjugateBayesianTensorFiltering,                # noqa: F401
                           NonconjugateBayesianTensorFiltering)
 from ._lib import BTFError, BTFLibraryError, NotPositiveDefiniteError                    # noqa: F401
+from .metrics import HeldOutEvaluator, heldout_classes                                      # noqa: F401
+from .datasets import load_politics, load_flu_states                                     # noqa: F401
 from .utils import ilogit, mse, mae, bayes_grid_penalty                                  # noqa: F401
 
 __version__ = '0.1.0'

@@ -75,6 +75,11 @@ SIGNATURES = {
     'btf_init_state': (C.c_int, [_P, C.c_int32]),
     'btf_mu_stats_track': (C.c_int, [_P, C.c_int32]),
     'btf_mu_stats_get': (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),
+    'btf_eval_set': (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    'btf_eval_clear': (C.c_int, [_P, C.c_int32]),
+    'btf_eval_update': (C.c_int, [_P, C.c_int32]),
+    'btf_eval_samples': (C.c_int, [_P, C.c_int32, _P, C.POINTER(C.c_int64)]),
+    'btf_eval_summary': (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     'btf_host_alloc': (_P, [C.c_size_t]),
     'btf_host_free': (None, [_P]),
     'btf_host_register': (C.c_int, [_P, C.c_size_t]),

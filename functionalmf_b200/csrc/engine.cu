@@ -38,6 +38,18 @@ struct DevBuf {
 
 enum Phase { PH_NU2 = 0, PH_SIGMA2, PH_TAU2, PH_LAM2, PH_ROW_STATS, PH_ROW_SOLVE, PH_COL_STATS, PH_BAND_SOLVE, PH_COMM, PH_COUNT };
 
+// one held-out evaluator (eval_kernels.cu)
+struct EvalSlot {
+    bool active = false, auto_update = false;
+    int ncls = 1, transform = 0, loglik = 0;
+    double* target = nullptr; uint8_t* cls = nullptr;
+    double *mean = nullptr, *below = nullptr, *above = nullptr, *cdf = nullptr;
+    unsigned *c_lt = nullptr, *c_le = nullptr;
+    double *partial = nullptr, *samples = nullptr, *summary = nullptr;
+    long long count = 0, max_samples = 0;
+};
+constexpr int EVAL_SLOTS = 4;
+
 struct btf_engine {
     btf_config cfg;
     int N, M, T, K, order, q, kd, RD, L, nco, P, Ppad, nloc, nloc_pad, n;
@@ -69,6 +81,7 @@ struct btf_engine {
     double *row_stats = nullptr, *col_stats = nullptr;
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
+    EvalSlot eval[EVAL_SLOTS];
     // workspaces
     double *work_L = nullptr, *work_y = nullptr, *partials = nullptr, *lam_partials = nullptr, *resid_partials = nullptr;
     size_t partials_n = 0;
@@ -296,6 +309,12 @@ static void free_graph(btf_engine* e) {
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
 }
 
+static void eval_free(EvalSlot& s) {
+    void* ptrs[] = {s.target, s.cls, s.mean, s.below, s.above, s.cdf, s.c_lt, s.c_le, s.partial, s.samples, s.summary};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s = EvalSlot();
+}
+
 void btf_destroy(btf_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
@@ -307,6 +326,7 @@ void btf_destroy(btf_engine* e) {
                     e->row_stats, e->col_stats, e->zbuf, e->mu_mean, e->mu_m2, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < EVAL_SLOTS; ++i) eval_free(e->eval[i]);
     for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : e->diagbuf) if (kv.second.p) cudaFree(kv.second.p);
     if (e->pinned_scal) cudaFreeHost(e->pinned_scal);
@@ -914,6 +934,8 @@ int btf_synchronize(btf_engine* e) {
     return BTF_OK;
 }
 
+static int eval_enqueue(btf_engine* e, int slot);
+
 __global__ void pack_scalars_kernel(const Scalars* s, double* out) {
     out[0] = s->sigma2; out[1] = s->lam2; out[2] = s->nu2; out[3] = s->lam2_a;
 }
@@ -941,6 +963,8 @@ int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t 
                                   (double)e->mu_count, e->stream);
                 e->launches++;
             }
+            for (int sl = 0; sl < EVAL_SLOTS; ++sl)
+                if (e->eval[sl].active && e->eval[sl].auto_update) { rc = eval_enqueue(e, sl); if (rc) return rc; }
             // snapshot on the compute stream (device-to-device), drain on the copy stream
             if (pending) CK(cudaStreamWaitEvent(e->stream, e->ev_copied, 0));
             if (W_out) CK(cudaMemcpyAsync(e->snapW, e->W, wn * 8, cudaMemcpyDeviceToDevice, e->stream));
@@ -1005,6 +1029,117 @@ int btf_mu_stats_get(btf_engine* e, double* mean_out, double* var_out, int64_t* 
         const double sc = e->mu_count > 1 ? 1.0 / (double)(e->mu_count - 1) : 0.0;
         for (size_t i = 0; i < n; ++i) var_out[i] *= sc;
     }
+    return BTF_OK;
+}
+
+// ------------------------------------------------------------------ held-out evaluation
+// (politics/benchmark.py:163-180, flutrends/benchmark.py:129-143,
+//  examples/poisson_tensor_filtering.py:20-23; kernels in eval_kernels.cu)
+static EvalArgs eval_args(btf_engine* e, EvalSlot& s) {
+    EvalArgs a{};
+    a.W = e->W + (size_t)e->cfg.row_begin * e->K; a.V = e->V;
+    a.K = e->K; a.nloc = e->nloc; a.P = e->P; a.T = e->T; a.row_begin = e->cfg.row_begin;
+    a.target = s.target; a.cls = s.cls; a.ncls = s.ncls; a.transform = s.transform; a.loglik = s.loglik;
+    a.Rdisp = e->Rdisp; a.Rn = e->Rn; a.Rm = e->Rm; a.Rt = e->Rt;
+    a.scal = e->scal; a.count = (double)s.count;
+    a.mean = s.mean; a.below = s.below; a.above = s.above; a.cdf = s.cdf; a.c_lt = s.c_lt; a.c_le = s.c_le;
+    a.partial = s.partial;
+    return a;
+}
+static int eval_enqueue(btf_engine* e, int slot) {
+    EvalSlot& s = e->eval[slot];
+    if (s.count >= s.max_samples) return set_err(BTF_ESTATE, "evaluator is full (max_samples reached)");
+    s.count += 1;
+    launch_eval_update(eval_args(e, s), s.samples + (size_t)(s.count - 1) * s.ncls * 4, e->stream);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return BTF_OK;
+}
+
+int btf_eval_set(btf_engine* e, int32_t slot, const double* target, const uint8_t* cls, int32_t nclasses,
+                 int32_t transform, int32_t loglik, int32_t cell_state, int32_t auto_update, int64_t max_samples) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    if (slot < 0 || slot >= EVAL_SLOTS) return set_err(BTF_EINVAL, "evaluator slot out of range");
+    if (!target) return set_err(BTF_EINVAL, "null target");
+    if (nclasses < 1 || nclasses > EVAL_MAX_CLASSES) return set_err(BTF_EINVAL, "1..4 classes");
+    if (transform < EVAL_IDENTITY || transform > EVAL_NB_MEAN) return set_err(BTF_EINVAL, "unknown mean transform");
+    if (transform == EVAL_NB_MEAN && !e->Rdisp) return set_err(BTF_EINVAL, "the NB mean needs a negative-binomial engine");
+    if (loglik < EVAL_LL_NONE || loglik > EVAL_LL_POISSON) return set_err(BTF_EINVAL, "unknown log-likelihood");
+    if (max_samples < 1) return set_err(BTF_EINVAL, "max_samples must be positive");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    EvalSlot& s = e->eval[slot];
+    eval_free(s);
+    const size_t n = (size_t)e->nloc * e->P;
+    s.ncls = nclasses; s.transform = transform; s.loglik = loglik; s.max_samples = max_samples;
+    s.auto_update = auto_update != 0;
+    CK(dev_alloc(&s.target, n, false));
+    CK(cudaMemcpy(s.target, target, n * 8, cudaMemcpyDefault));
+    if (cls) { CK(dev_alloc(&s.cls, n, false)); CK(cudaMemcpy(s.cls, cls, n, cudaMemcpyDefault)); }
+    if (cell_state) {
+        CK(dev_alloc(&s.mean, n)); CK(dev_alloc(&s.below, n, false)); CK(dev_alloc(&s.above, n, false));
+        CK(dev_alloc(&s.c_lt, n)); CK(dev_alloc(&s.c_le, n));
+        if (cell_state > 1) CK(dev_alloc(&s.cdf, n));
+        launch_eval_init(s.below, s.above, (long long)n, e->stream);
+        e->launches++;
+    }
+    const long long pe = std::max<long long>(eval_partial_elems(e->nloc, e->P, nclasses),
+                                             (long long)eval_summary_blocks(e->nloc, e->P) * nclasses * 6);
+    CK(dev_alloc(&s.partial, (size_t)pe));
+    CK(dev_alloc(&s.samples, (size_t)max_samples * nclasses * 4));
+    CK(dev_alloc(&s.summary, (size_t)nclasses * 6));
+    CK(cudaStreamSynchronize(e->stream));
+    s.active = true;
+    return BTF_OK;
+}
+
+int btf_eval_clear(btf_engine* e, int32_t slot) {
+    if (!e) return set_err(BTF_EINVAL, "null engine");
+    if (slot < 0 || slot >= EVAL_SLOTS) return set_err(BTF_EINVAL, "evaluator slot out of range");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    eval_free(e->eval[slot]);
+    return BTF_OK;
+}
+
+#define EVAL_SLOT_OR_FAIL(e, slot)                                                              \
+    if (!e) return set_err(BTF_EINVAL, "null engine");                                          \
+    if (slot < 0 || slot >= EVAL_SLOTS || !e->eval[slot].active)                                \
+        return set_err(BTF_ESTATE, "no evaluator in this slot (btf_eval_set first)");          \
+    CK(cudaSetDevice(e->cfg.device));
+
+// score the current device state as one more sample
+int btf_eval_update(btf_engine* e, int32_t slot) {
+    EVAL_SLOT_OR_FAIL(e, slot)
+    return eval_enqueue(e, slot);
+}
+
+// out: [count][nclasses][4] = {n, sum (y - mu)^2, sum |y - mu|, sum loglik} per scored sample
+int btf_eval_samples(btf_engine* e, int32_t slot, double* out, int64_t* count_out) {
+    EVAL_SLOT_OR_FAIL(e, slot)
+    EvalSlot& s = e->eval[slot];
+    CK(cudaStreamSynchronize(e->stream));
+    if (count_out) *count_out = s.count;
+    if (out && s.count) CK(cudaMemcpy(out, s.samples, (size_t)s.count * s.ncls * 4 * 8, cudaMemcpyDeviceToHost));
+    return BTF_OK;
+}
+
+// out: [nclasses][6] = {n, sum (y - mean)^2, sum |y - mean|, sum loglik(y | mean), # cells whose target lies
+// inside the [lo_pct, hi_pct] percentile band of the scored samples (np.percentile, linear interpolation),
+// # cells with pred_lo <= mean_s Phi((y - mu_s) / sqrt(nu2_s)) <= pred_hi}; mean_out (optional): [Nloc, M, T]
+int btf_eval_summary(btf_engine* e, int32_t slot, double lo_pct, double hi_pct, double pred_lo, double pred_hi,
+                     double* out, double* mean_out) {
+    EVAL_SLOT_OR_FAIL(e, slot)
+    EvalSlot& s = e->eval[slot];
+    if (!s.mean) return set_err(BTF_ESTATE, "the evaluator keeps no per-cell state (cell_state = 0)");
+    if (s.count < 1) return set_err(BTF_ESTATE, "no sample has been scored yet");
+    if (!(lo_pct >= 0.0 && lo_pct <= hi_pct && hi_pct <= 100.0)) return set_err(BTF_EINVAL, "0 <= lo_pct <= hi_pct <= 100");
+    launch_eval_summary(eval_args(e, s), lo_pct, hi_pct, pred_lo, pred_hi, s.partial, s.summary, e->stream);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    if (out) CK(cudaMemcpy(out, s.summary, (size_t)s.ncls * 6 * 8, cudaMemcpyDeviceToHost));
+    if (mean_out) CK(cudaMemcpy(mean_out, s.mean, (size_t)e->nloc * e->P * 8, cudaMemcpyDeviceToHost));
     return BTF_OK;
 }
 

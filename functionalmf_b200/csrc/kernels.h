@@ -51,6 +51,31 @@ void launch_residual(const uint8_t* cnt, const double* S, long long ld, const do
 void launch_mu_moments(const double* W, const double* V, int K, int nloc, int P, double* mean, double* m2,
                        double count, cudaStream_t st);
 
+// ---------------------------------------------------------------- held-out evaluation (eval_kernels.cu)
+enum { EVAL_IDENTITY = 0, EVAL_ILOGIT = 1, EVAL_NB_MEAN = 2 };
+enum { EVAL_LL_NONE = 0, EVAL_LL_GAUSSIAN = 1, EVAL_LL_POISSON = 2 };
+constexpr int EVAL_MAX_CLASSES = 4;
+struct EvalArgs {
+    const double* W; const double* V;      // W already offset to the local row block
+    int K, nloc, P, T, row_begin;
+    const double* target;                  // [nloc][P], NaN = not scored
+    const uint8_t* cls; int ncls;          // class per cell (>= ncls: not scored) or nullptr (all class 0)
+    int transform, loglik;
+    const double* Rdisp; int Rn, Rm, Rt;   // NB dispersion (EVAL_NB_MEAN)
+    const Scalars* scal;                   // nu2 of the current sample (Gaussian log-likelihood / predictive cdf)
+    double count;                          // samples seen including this one
+    double *mean, *below, *above, *cdf;    // per-cell state, all nullptr when not kept (cdf optional)
+    unsigned *c_lt, *c_le;
+    double* partial;                       // per-block partial sums
+};
+long long eval_partial_elems(int nloc, int P, int ncls);
+// one saved sample: sample_out[c][4] = {n, sum (y-mu)^2, sum |y-mu|, sum loglik}; 2 launches
+void launch_eval_update(const EvalArgs& a, double* sample_out, cudaStream_t st);
+void launch_eval_init(double* below, double* above, long long n, cudaStream_t st);
+int eval_summary_blocks(int nloc, int P);
+void launch_eval_summary(const EvalArgs& a, double lo_pct, double hi_pct, double lo_frac, double hi_frac,
+                         double* partial, double* out, cudaStream_t st);
+
 // ---------------------------------------------------------------- K2 row solve
 struct RowSolveArgs {
     const double* stats;   // [nsplit][nloc][L+K]

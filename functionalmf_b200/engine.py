@@ -171,6 +171,41 @@ class Engine(object):
         L.check(self.lib.btf_mu_stats_get(self._h, _ptr(mean), _ptr(var), C.byref(cnt)))
         return mean, var, int(cnt.value)
 
+    # ---- held-out evaluation (btf_eval_*)
+    def eval_set(self, slot, target, classes=None, nclasses=1, transform=0, loglik=0, cell_state=1,
+                 auto_update=True, max_samples=1000):
+        shape = (self.nloc, self.M, self.T)
+        t = _f64(target)
+        if t.shape != shape:
+            raise ValueError('target must have the local shape %r, got %r' % (shape, t.shape))
+        c = None
+        if classes is not None:
+            c = np.ascontiguousarray(classes, dtype=np.uint8)
+            if c.shape != shape:
+                raise ValueError('classes must have the local shape %r, got %r' % (shape, c.shape))
+        L.check(self.lib.btf_eval_set(self._h, int(slot), _ptr(t), _ptr(c), int(nclasses), int(transform),
+                                      int(loglik), int(cell_state), 1 if auto_update else 0, int(max_samples)))
+
+    def eval_clear(self, slot):
+        L.check(self.lib.btf_eval_clear(self._h, int(slot)))
+
+    def eval_update(self, slot):
+        L.check(self.lib.btf_eval_update(self._h, int(slot)))
+
+    def eval_samples(self, slot, nclasses):
+        cnt = C.c_int64(0)
+        L.check(self.lib.btf_eval_samples(self._h, int(slot), C.c_void_p(0), C.byref(cnt)))
+        out = np.empty((int(cnt.value), int(nclasses), 4), dtype=np.float64)
+        L.check(self.lib.btf_eval_samples(self._h, int(slot), _ptr(out), C.byref(cnt)))
+        return out
+
+    def eval_summary(self, slot, nclasses, lo_pct, hi_pct, pred_lo=0.0, pred_hi=1.0, want_mean=False):
+        out = np.empty((int(nclasses), 6), dtype=np.float64)
+        mean = np.empty((self.nloc, self.M, self.T), dtype=np.float64) if want_mean else None
+        L.check(self.lib.btf_eval_summary(self._h, int(slot), float(lo_pct), float(hi_pct), float(pred_lo),
+                                          float(pred_hi), _ptr(out), _ptr(mean)))
+        return (out, mean) if want_mean else out
+
     def synchronize(self):
         L.check(self.lib.btf_synchronize(self._h))
 

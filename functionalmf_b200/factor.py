@@ -50,6 +50,8 @@ class _BayesianModel(object):
         self._begin(data)
         if track_mu:
             self._engine.track_mu_stats(True)
+        for ev in getattr(self, '_evaluators', {}).values():
+            ev._arm(nsamples)        # HeldOutEvaluator (metrics.py): every saved sample is scored on the device
         results = self._alloc_results(nsamples)
         outs = self._result_buffers(results)
         seg = max(1, int(print_freq)) if verbose else nsteps
@@ -76,6 +78,9 @@ class _BayesianModel(object):
     def _run_gibbs_callback(self, data, nburn, nthin, nsamples, verbose, print_freq, callback, **kwargs):
         nsteps = nburn + nthin * nsamples
         results = None
+        evaluators = list(getattr(self, '_evaluators', {}).values())
+        for ev in evaluators:
+            ev._arm(nsamples)
         for step in range(nsteps):
             if verbose and step % print_freq == 0:
                 print('\tStep {}'.format(step))
@@ -90,6 +95,8 @@ class _BayesianModel(object):
                         results[key] = np.zeros([nsamples] + ([1] if np.isscalar(val) else list(np.shape(val))))
                 for key, val in inferred.items():
                     results[key][sidx] = val
+                for ev in evaluators:
+                    ev.update()
         return results
 
 

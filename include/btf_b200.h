@@ -115,6 +115,30 @@ int btf_synchronize(btf_engine* e);
  * genlasso.py:51-65).  mean_out / var_out: [Nloc, M, T], either may be NULL. */
 int btf_mu_stats_track(btf_engine* e, int32_t track);
 int btf_mu_stats_get(btf_engine* e, double* mean_out, double* var_out, int64_t* count_out);
+/* Held-out evaluation on the device.  Replaces the numpy scoring of the saved
+ * samples in politics/benchmark.py:163-180 (per-sample RMSE / MAE / Poisson log-likelihood of the NB
+ * mean, in-sample vs held-out), flutrends/benchmark.py:129-143 (RMSE / MAE of the posterior mean,
+ * coverage of the predictive band, 68-75) and examples/poisson_tensor_filtering.py:20-23
+ * (coverage_at: truth inside the central np.percentile band of the samples).
+ *   target [Nloc, M, T]  value to score against, NaN = not scored
+ *   cls    [Nloc, M, T]  class of every cell (0 .. nclasses-1; anything else = not scored), NULL = all 0
+ *   transform  0 identity, 1 ilogit(psi), 2 NB mean R P / (1 - P) with P = ilogit(clip(psi, -10, 10))
+ *   loglik     0 none, 1 Gaussian with the sample's nu2, 2 Poisson
+ *   cell_state 0 per-sample sums only; 1 + per-cell running mean and percentile-band state (40 B/cell);
+ *              2 + mixture cdf for the Gaussian posterior-predictive band
+ *   auto_update != 0: every sample saved by btf_run / btf_run_segment is scored
+ * Up to 4 evaluators (slots 0..3) per engine.  Sums are over the LOCAL rows; ranks add them up. */
+int btf_eval_set(btf_engine* e, int32_t slot, const double* target, const uint8_t* cls, int32_t nclasses,
+                 int32_t transform, int32_t loglik, int32_t cell_state, int32_t auto_update, int64_t max_samples);
+int btf_eval_clear(btf_engine* e, int32_t slot);
+int btf_eval_update(btf_engine* e, int32_t slot);
+/* out [count, nclasses, 4] = {n, sum (y-mu)^2, sum |y-mu|, sum loglik} per scored sample */
+int btf_eval_samples(btf_engine* e, int32_t slot, double* out, int64_t* count_out);
+/* out [nclasses, 6] = {n, sum (y-mean)^2, sum |y-mean|, sum loglik(y|mean), # targets inside the
+ * [lo_pct, hi_pct] percentile band of the samples, # targets with pred_lo <= predictive cdf <= pred_hi};
+ * mean_out (optional) [Nloc, M, T] posterior mean of the transformed surface */
+int btf_eval_summary(btf_engine* e, int32_t slot, double lo_pct, double hi_pct, double pred_lo, double pred_hi,
+                     double* out, double* mean_out);
 /* Constructor draws from the priors on the device (factor.py:230-253, 293-304, 560-563;
  * utils.py:115-124).  init_mask bits: 1 sigma2, 2 lam2, 4 nu2, 8 Tau2, 16 W, 32 V, 64 R. */
 int btf_init_state(btf_engine* e, int32_t init_mask);

@@ -39,7 +39,7 @@ def run(name, eng, nsweeps, warm=5, extra=None):
 
 def main():
     rs = np.random.RandomState(0)
-    which = sys.argv[1:] or ['c1', 'c4', 'k32', 'c3']
+    which = sys.argv[1:] or ['c1', 'c4', 'k32', 'c3', 'eval']
     if 'c1' in which:
         N, M, T, K = 11, 12, 20, 3
         W, V = truth(rs, N, M, T, K)
@@ -107,6 +107,31 @@ def main():
         st = o['phases_ms']['row_stats'] + o['phases_ms']['col_stats']
         print(json.dumps(dict(c3_stats_tflops=fl / (st * 1e-3) / 1e12,
                               c3_pg_draws_per_s=cells * 4 / (o['phases_ms']['nu2_or_pg'] * 1e-3))), flush=True)
+        eng.close()
+
+    if 'eval' in which:
+        # held-out evaluator (eval_kernels.cu) at the C2 cell count: one scoring pass per saved sample
+        N, M, T, K = 4096, 1024, 64, 16
+        W, V = truth(rs, N, M, T, K)
+        eng = Engine(N, M, T, nembeds=K, tf_order=2, seed=1)
+        eng.set('W', W); eng.set('V', V); eng.set('nu2', [1.0])
+        target = np.einsum('nk,mtk->nmt', W, V) + rs.normal(size=(N, M, T))
+        cls = (rs.random_sample((N, M, T)) < 0.1).astype(np.uint8)
+        cells = N * M * T
+        for state, bpc in ((0, 9), (1, 9 + 2 * 32), (2, 9 + 2 * 40)):
+            eng.eval_set(0, target, cls, nclasses=2, loglik=1, cell_state=state, auto_update=False, max_samples=64)
+            for _ in range(3):
+                eng.eval_update(0)
+            eng.synchronize()
+            t0 = time.time()
+            for _ in range(20):
+                eng.eval_update(0)
+            eng.synchronize()
+            dt = (time.time() - t0) / 20
+            print(json.dumps(dict(config='held-out evaluator, 4096x1024x64 cells K16, cell_state=%d' % state,
+                                  ms_per_sample=dt * 1e3, algorithmic_bytes_per_cell=bpc,
+                                  gb_per_s=cells * bpc / dt / 1e9)), flush=True)
+            eng.eval_clear(0)
         eng.close()
 
 

@@ -44,6 +44,14 @@ def main():
         eng.sweep(3)
         got = {k: eng.get(k) for k in ('W', 'V', 'Tau2')}
         got.update({k: eng.get_scalar(k) for k in ('nu2', 'sigma2', 'lam2')})
+        # held-out evaluator: local sums add up to the single-GPU sums
+        target = np.nanmean(Y, axis=-1) if R > 1 else Y[..., 0]
+        cls = (np.arange(N * M * T).reshape(N, M, T) % 3 == 0).astype(np.uint8)
+        eng.eval_set(0, target[r0:r1], cls[r0:r1], nclasses=2, loglik=1, cell_state=1, auto_update=False, max_samples=2)
+        eng.eval_update(0)
+        ev = torch.from_numpy(eng.eval_samples(0, 2)).cuda()
+        dist.all_reduce(ev)
+        ev = ev.cpu().numpy()
         ms = eng.sweep_timed(5)
         eng.close()
         torch.cuda.synchronize()
@@ -59,6 +67,10 @@ def main():
                 worst = max(worst, float(np.max(np.abs(a - b)) / np.max(np.abs(b))))
             for k in ('nu2', 'sigma2', 'lam2'):
                 worst = max(worst, abs(got[k] - ref.get_scalar(k)) / abs(ref.get_scalar(k)))
+            ref.eval_set(0, target, cls, nclasses=2, loglik=1, cell_state=1, auto_update=False, max_samples=2)
+            ref.eval_update(0)
+            ev1 = ref.eval_samples(0, 2)
+            worst = max(worst, float(np.max(np.abs(ev - ev1) / np.abs(ev1))))
             ms1 = ref.sweep_timed(5)
             ref.close()
             good = worst < 1e-8
