@@ -56,11 +56,14 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
 
 }  // namespace
 
-// 64 rows x 256 cells per block, like the residual / moments passes.
-template <int KMAX>
-__global__ void __launch_bounds__(256) eval_update_kernel(EvalArgs a) {
+// 64 rows x 256 cells per block: thread = one (column, depth) cell position p with its V row in
+// registers, walking the block's rows in batches whose loads are all issued before any is used
+// (one load round trip per batch instead of per cell: the pass is latency bound otherwise).
+template <int KMAX, bool STATE>
+__global__ void __launch_bounds__(256, KMAX <= 16 ? 2 : 1) eval_update_kernel(EvalArgs a) {
+    constexpr int B = STATE ? 4 : 8;
     __shared__ double ws[64 * KMAX];
-    __shared__ double red[32];
+    __shared__ double red[8][EVAL_MAX_CLASSES * 4];
     const int K = a.K;
     const int p = blockIdx.x * 256 + threadIdx.x;
     const int i0 = blockIdx.y * 64;
@@ -71,55 +74,92 @@ __global__ void __launch_bounds__(256) eval_update_kernel(EvalArgs a) {
     for (int k = 0; k < KMAX; ++k) v[k] = (k < K && p < a.P) ? a.V[(long long)p * K + k] : 0.0;
     __syncthreads();
     const double nu2 = a.scal->nu2;
-    const double inv_sd = rsqrt(nu2);
+    const double inv_sd = rsqrt(nu2), inv_nu2 = 1.0 / nu2, lognorm = log(6.283185307179586477 * nu2);
     const double inv_count = 1.0 / a.count;
+    const bool live = p < a.P;
     double acc[EVAL_MAX_CLASSES][4];
+    unsigned ncell[EVAL_MAX_CLASSES];
 #pragma unroll
-    for (int c = 0; c < EVAL_MAX_CLASSES; ++c)
+    for (int c = 0; c < EVAL_MAX_CLASSES; ++c) {
+        ncell[c] = 0u;
 #pragma unroll
         for (int m = 0; m < 4; ++m) acc[c][m] = 0.0;
-    if (p < a.P) {
-        for (int r = 0; r < nr; ++r) {
+    }
+    for (int r0 = 0; r0 < nr; r0 += B) {
+        double yv[B];
+        int cv[B];
+        double mv[B], bv[B], av[B], fv[B];
+        unsigned ltv[B], lev[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const bool ok = live && r0 + u < nr;
+            const long long o = (long long)(i0 + r0 + u) * a.P + p;
+            yv[u] = ok ? a.target[o] : NAN;
+            cv[u] = ok ? (a.cls ? (int)a.cls[o] : 0) : 255;
+        }
+        if (STATE) {
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const long long o = (long long)(i0 + r0 + u) * a.P + p;
+                const bool on = yv[u] == yv[u] && cv[u] < a.ncls;
+                mv[u] = on ? a.mean[o] : 0.0;
+                bv[u] = on ? a.below[o] : 0.0;
+                av[u] = on ? a.above[o] : 0.0;
+                ltv[u] = on ? a.c_lt[o] : 0u;
+                lev[u] = on ? a.c_le[o] : 0u;
+                fv[u] = (on && a.cdf) ? a.cdf[o] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const double y = yv[u];
+            const int cl = cv[u];
+            if (y != y || cl >= a.ncls) continue;
+            const int r = r0 + u;
             const long long o = (long long)(i0 + r) * a.P + p;
-            const double y = a.target[o];
-            if (y != y) continue;
-            const int cl = a.cls ? (int)a.cls[o] : 0;
-            if (cl >= a.ncls) continue;
             double psi = 0.0;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k)
                 if (k < K) psi += ws[r * K + k] * v[k];
             const double mu = eval_transform(a, psi, i0 + r, p);
             const double d = y - mu;
-            const double ll = eval_loglik(a.loglik, y, mu, nu2);
+            double ll = 0.0;
+            if (a.loglik == EVAL_LL_GAUSSIAN) ll = -0.5 * (lognorm + d * d * inv_nu2);
+            else if (a.loglik == EVAL_LL_POISSON) ll = eval_loglik(EVAL_LL_POISSON, y, mu, nu2);
 #pragma unroll
             for (int c = 0; c < EVAL_MAX_CLASSES; ++c) {
                 const bool on = cl == c;
-                acc[c][0] += on ? 1.0 : 0.0;
+                ncell[c] += on ? 1u : 0u;
                 acc[c][1] += on ? d * d : 0.0;
                 acc[c][2] += on ? fabs(d) : 0.0;
                 acc[c][3] += on ? ll : 0.0;
             }
-            if (a.mean) {
-                const double m = a.mean[o];
-                a.mean[o] = m + (mu - m) * inv_count;
-                if (mu < y) { a.c_lt[o] += 1; a.c_le[o] += 1; if (mu > a.below[o]) a.below[o] = mu; }
-                else if (mu == y) a.c_le[o] += 1;
-                else if (mu < a.above[o]) a.above[o] = mu;
-                if (a.cdf) a.cdf[o] += 0.5 * erfc(-(d * inv_sd) * 0.70710678118654752440);
+            if (STATE) {
+                a.mean[o] = mv[u] + (mu - mv[u]) * inv_count;
+                if (mu < y) {
+                    a.c_lt[o] = ltv[u] + 1; a.c_le[o] = lev[u] + 1;
+                    if (mu > bv[u]) a.below[o] = mu;
+                } else if (mu == y) a.c_le[o] = lev[u] + 1;
+                else if (mu < av[u]) a.above[o] = mu;
+                if (a.cdf) a.cdf[o] = fv[u] + 0.5 * erfc(-(d * inv_sd) * 0.70710678118654752440);
             }
         }
     }
-    double* out = a.partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * (a.ncls * 4);
-    for (int c = 0; c < a.ncls; ++c)
+    // fixed-order block reduction: warp shuffles, then the 8 warp partials in order
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < EVAL_MAX_CLASSES; ++c)
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            double val = 0.0;
-#pragma unroll
-            for (int cc = 0; cc < EVAL_MAX_CLASSES; ++cc) val = cc == c ? acc[cc][m] : val;
-            const double s = block_sum(val, red);
-            if (threadIdx.x == 0) out[c * 4 + m] = s;
+            const double sw = warp_sum(m == 0 ? (double)ncell[c] : acc[c][m]);
+            if (lane == 0) red[w][c * 4 + m] = sw;
         }
+    __syncthreads();
+    if (threadIdx.x < a.ncls * 4) {
+        double sum = 0.0;
+        for (int ww = 0; ww < 8; ++ww) sum += red[ww][threadIdx.x];
+        a.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * (a.ncls * 4) + threadIdx.x] = sum;
+    }
 }
 
 // out[v] = sum_b partial[b][v] in a fixed order; one block per output value
@@ -135,9 +175,15 @@ __global__ void __launch_bounds__(256) eval_reduce_kernel(const double* __restri
 
 void launch_eval_update(const EvalArgs& a, double* sample_out, cudaStream_t st) {
     dim3 grid((a.P + 255) / 256, (a.nloc + 63) / 64);
-    if (a.K <= 8) eval_update_kernel<8><<<grid, 256, 0, st>>>(a);
-    else if (a.K <= 16) eval_update_kernel<16><<<grid, 256, 0, st>>>(a);
-    else eval_update_kernel<32><<<grid, 256, 0, st>>>(a);
+    if (a.mean) {
+        if (a.K <= 8) eval_update_kernel<8, true><<<grid, 256, 0, st>>>(a);
+        else if (a.K <= 16) eval_update_kernel<16, true><<<grid, 256, 0, st>>>(a);
+        else eval_update_kernel<32, true><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (a.K <= 8) eval_update_kernel<8, false><<<grid, 256, 0, st>>>(a);
+        else if (a.K <= 16) eval_update_kernel<16, false><<<grid, 256, 0, st>>>(a);
+        else eval_update_kernel<32, false><<<grid, 256, 0, st>>>(a);
+    }
     eval_reduce_kernel<<<a.ncls * 4, 256, 0, st>>>(a.partial, (int)(grid.x * grid.y), a.ncls * 4, sample_out);
 }
 long long eval_partial_elems(int nloc, int P, int ncls) {

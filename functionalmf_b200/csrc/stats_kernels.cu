@@ -832,19 +832,31 @@ __global__ void __launch_bounds__(256) mu_moments_kernel(const double* __restric
     __syncthreads();
     if (p >= P) return;
     const double inv = 1.0 / count;
-    for (int r = 0; r < 64; ++r) {
-        const int il = i0 + r;
-        if (il >= nloc) break;
-        double mu = 0.0;
+    const int nr = min(64, nloc - i0);
+    // batches of 4 rows: all loads of a batch are in flight before the first update
+    for (int r0 = 0; r0 < nr; r0 += 4) {
+        double m[4], q[4];
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-            if (k < K) mu += ws[r * K + k] * v[k];
-        const long long o = (long long)il * P + p;
-        const double m = mean[o];
-        const double d = mu - m;
-        const double mn = m + d * inv;
-        mean[o] = mn;
-        m2[o] += d * (mu - mn);
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = r0 + u < nr;
+            const long long o = (long long)(i0 + r0 + u) * P + p;
+            m[u] = ok ? mean[o] : 0.0;
+            q[u] = ok ? m2[o] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u;
+            if (r >= nr) break;
+            double mu = 0.0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) mu += ws[r * K + k] * v[k];
+            const long long o = (long long)(i0 + r) * P + p;
+            const double d = mu - m[u];
+            const double mn = m[u] + d * inv;
+            mean[o] = mn;
+            m2[o] = q[u] + d * (mu - mn);
+        }
     }
 }
 

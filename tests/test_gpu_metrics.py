@@ -36,7 +36,7 @@ def test_politics_golden_replay(gold):
     S, N, K = Ws.shape
     M, T = Vs.shape[1:3]
     model = NegativeBinomialBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=2, sigma2_init=0.5,
-                                                    lam2_init=0.1, seed=3)
+                                                    lam2_init=0.1, rdims=(), seed=3)    # one R per cell
     ev = HeldOutEvaluator(model, gold['pol_Y'], train=gold['pol_Y_train'], transform='nb_mean',
                           loglik='poisson', max_samples=S)
     _replay(model, ev, Ws, Vs, Rs=Rs)
