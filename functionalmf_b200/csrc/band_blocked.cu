@@ -21,6 +21,8 @@
 // The live window is the lower triangle of a (Q+1) x (Q+1) block grid; diagonal d of that
 // grid is a circular buffer of Q+1-d blocks (slot = base_d + row mod (Q+1-d)), so the window
 // advances without copying: the entering row overwrites exactly the retired column blocks.
+#include <cstdio>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace btf {
@@ -109,6 +111,13 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
     const bool have_stats = a.stats != nullptr;
     const double* stats0 = have_stats ? a.stats + (size_t)jg * T * nco : nullptr;
 
+#ifdef BTF_BAND_PROFILE
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long c0 = clock64(), c1;
+#define PROF(i) do { c1 = clock64(); pc[i] += c1 - c0; c0 = c1; } while (0)
+#else
+#define PROF(i)
+#endif
     double jitter = 0.0, eps = a.eps;
     int attempt = 0;
     bool failed = false;
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
         // ---- initial window: block rows 0..Q
         for (int r = 0; r <= Q && r < T; ++r) init_row(r, tid, NT);
         __syncthreads();
+        PROF(0);
         bool broke = false;
         for (int t = 0; t < T; ++t) {
             // ================= P1: potrf of the diagonal block (warp 0)  ||  P4 of step t-1
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 init_row(t + Q, tid - 32, NT - 32);
             }
             __syncthreads();
+            PROF(1);
             if (fail_flag) { broke = true; break; }
 
             // ================= P2: triangular solves against L_tt (one thread per row)
@@ -236,6 +247,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 }
             }
             __syncthreads();
+            PROF(2);
 
             // ================= P3: trailing update, right-hand side update, spill block column t
             if (active && !is_rhs) {
@@ -291,6 +303,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
                 }
             }
             __syncthreads();
+            PROF(3);
         }
         if (!broke) break;
         __syncthreads();
@@ -372,6 +385,7 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
     }
     cp_wait<0>();
     __syncthreads();
+    PROF(4);
 
     // ---- nu2 by-product: sum_t v_t^T A_t v_t - 2 v_t . b_t with the UNSCALED statistics
     if (a.resid_partials && have_stats) {
@@ -415,6 +429,12 @@ __global__ void __launch_bounds__(BlkGeom<KB, Q>::NT, BlkGeom<KB, Q>::MINB) band
         double tot = block_sum(accum, red);
         if (tid == 0) a.resid_partials[jl] = tot;
     }
+    PROF(5);
+#ifdef BTF_BAND_PROFILE
+    if (tid == 0 && (jl == 0 || jl == a.ncols_loc - 1))
+        printf("band col %d: init %lld | potrf+assemble %lld | trsm %lld | trailing %lld | backward %lld | resid %lld cycles\n",
+               jl, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5]);
+#endif
 }
 
 template <int KB, int Q>
@@ -432,6 +452,9 @@ static void launch_blocked_t(const BandSolveArgs& a, cudaStream_t st) {
 }
 
 bool launch_band_solve_blocked(const BandSolveArgs& a, cudaStream_t st) {
+    // default: the look-ahead kernel (band_lookahead.cu); BTF_BAND_V1=1 keeps this file's kernel for A/B runs
+    static const bool v1 = getenv("BTF_BAND_V1") != nullptr;
+    if (!v1 && launch_band_solve_lookahead(a, st)) return true;
     const int Q = a.order + 1;
 #define BTF_BLK(KB_)                                                  \
     do {                                                              \
