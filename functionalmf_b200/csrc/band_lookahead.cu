@@ -16,6 +16,7 @@
 // Critical path per block column: one tensor-pipe solve, one KB x KB syrk tile row, one potrf.
 // Measured per column (K = 16, T = 64, one CTA per SM): see DESIGN.md K3.
 #include <cstdio>
+#include <type_traits>
 #include "kernels.h"
 
 namespace btf {
@@ -36,6 +37,18 @@ __device__ __forceinline__ void la_dmma(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// 1/d for the pivot chain: hardware seed (relative error < 2^-20) and ONE third-order step
+// y0 (1 + e + e^2), e = 1 - d y0  ->  relative error ~2^-60 plus rounding: three dependent FP64
+// operations instead of the five of an IEEE division (every FP64 operation on this chain costs
+// its full pipeline latency).  d is positive and finite here.
+__device__ __forceinline__ double la_rcp_pos(double d) {
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(y0) : "d"(d));
+    const double e = fma(-d, y0, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(e2, y0, y0);
+}
+
 template <int KB, int Q>
 struct LaGeom {
     static constexpr int KS = KB + 4;                      // padded row stride of a block in shared memory
@@ -50,12 +63,13 @@ struct LaGeom {
     static constexpr int COLE = (Q + 1) * KK;              // global block column: Linv_t | L_1t .. L_Qt
     static constexpr int BWD = COLE + KB;                  // + y_t : one backward stage
     static constexpr int WREG = NBLK * BLK > 2 * BWD ? NBLK * BLK : 2 * BWD;
+    static constexpr int NSW = TB <= 2 ? TB : 1;           // 8-row strips a worker warp runs together (independent tensor-pipe chains)
     static constexpr int PF = (KB * (KB + 1) / 2 + NWT - 1) / NWT;   // prefetched statistics per worker thread
     __host__ __device__ static constexpr int base(int d) { return d * (Q + 1) - d * (d - 1) / 2; }
     __device__ static __forceinline__ int slot(int a, int d) { return base(d) + a % (Q + 1 - d); }
     static size_t smem_doubles(int T, int RD) {
         return (size_t)WREG + 2 * BLK + (Q + 1) * KB + KB + 2 * (Q + 1) * KB + 2 * KB + 2 * KB + (size_t)T * (Q + 1) +
-               RD + 48 + (KB * (KB + 1) / 2 + 3) / 4;
+               RD + 48 + 96 + (KB * (KB + 1) / 2 + 3) / 4;
     }
 };
 
@@ -84,7 +98,9 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     double* Pband = zb + 2 * KB;                       // [T][Q+1]
     double* linv = Pband + (size_t)T * (Q + 1);        // [RD]
     double* red = linv + a.RD;                         // [40]
-    unsigned short* pairtab = reinterpret_cast<unsigned short*>(red + 40);   // [L] packed index -> (i << 8 | c)
+    double* colb = red + 48;                           // [2][32] pivot column of the potrf warp
+    double* dbuf = colb + 64;                          // [32]    pivots d_j, then 1/sqrt(d_j)
+    unsigned short* pairtab = reinterpret_cast<unsigned short*>(dbuf + 32);   // [L] packed index -> (i << 8 | c)
     __shared__ int fail_flag;
 
     const double scale = a.homoskedastic ? 1.0 / a.scal->nu2 : 1.0;
@@ -116,6 +132,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
 #ifdef BTF_BAND_PROFILE
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long wp[4] = {0, 0, 0, 0};
+    long long wq[4] = {0, 0, 0, 0};
     long long pc0 = clock64(), pc1;
 #define LAPROF(i) do { pc1 = clock64(); pc[i] += pc1 - pc0; pc0 = pc1; } while (0)
 #else
@@ -185,35 +202,41 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
             else if (AUG && lane - KB == c) v = 1.0;
             ar[c] = v;
         }
+        // The pivot chain runs on the UNSCALED columns (L D L^T form): with q_j = 1/d_j,
+        //   a_ik <- a_ik - (a_ij q_j) a_kj,   d_{j+1} = a_{j+1,j+1} - a_{j+1,j}^2 q_j  (own lane, no exchange).
+        // The loop is issue bound, so it is kept short: the pivot column goes through shared memory
+        // once (one store, broadcast reads) instead of one 64-bit shuffle pair per entry, the update
+        // is unconditional (entries above the diagonal are never read), and the square roots that turn
+        // column j into L_ij = a_ij / sqrt(d_j) are taken once, one per lane, after the loop.
         bool ok = true;
-        double mydinv = 1.0;
         double d = __shfl_sync(full, ar[0], 0);
         if (!(d > 0.0) || isinf(d)) ok = false;
-        double rinv = rsqrt(ok ? d : 1.0);
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
-            const double ljj = d * rinv;
-            const double lij = (lane == j) ? ljj : ar[j] * rinv;
-            ar[j] = lij;
-            if (lane == j) mydinv = rinv;
+            const double dj = ok ? d : 1.0;
+            const double aj = ar[j];
+            double* cb = colb + (j & 1) * 32;
+            cb[lane] = aj;
+            if (lane == 0) dbuf[j] = dj;
+            const double q = la_rcp_pos(dj);
             if (j + 1 < KB) {
-                // the next pivot first (its own lane needs no exchange): the reciprocal square root
-                // of pivot j+1 overlaps the rest of this column's update
-                const double dloc = ar[j + 1] - lij * lij;       // the value lane j+1 is about to hold
+                const double dloc = fma(-(aj * aj), q, ar[j + 1]);      // what lane j+1 is about to hold
                 d = __shfl_sync(full, dloc, j + 1);
                 if (!(d > 0.0) || isinf(d)) ok = false;
-                rinv = rsqrt(ok ? d : 1.0);
-                const double l1 = __shfl_sync(full, lij, j + 1);
-                if (lane >= j + 1) ar[j + 1] -= lij * l1;
             }
+            __syncwarp();
+            const double tq = -(aj * q);
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                if (k > j + 1) {            // rectangular loop + constant predicate: fully unrollable
-                    const double lkj = __shfl_sync(full, lij, k);
-                    if (lane >= k) ar[k] -= lij * lkj;
-                }
-            }
+            for (int k = 0; k < KB; ++k)
+                if (k > j) ar[k] = fma(tq, cb[k], ar[k]);   // rectangular loop + constant predicate: fully unrollable
         }
+        __syncwarp();
+        const double mydinv = rsqrt(dbuf[lane < KB ? lane : 0]);
+        __syncwarp();
+        if (lane < KB) dbuf[lane] = mydinv;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < KB; ++c) ar[c] *= dbuf[c];
         if (!ok && lane == 0) fail_flag = 1;
         if (lane < KB) {
 #pragma unroll
@@ -244,6 +267,92 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         }
     };
 
+    // C[8 rows of strip tm][all KB columns] -= A[strip tm] B^T  (SUB) or  = A[strip tm] Linv^T in place (!SUB):
+    // one warp, TB independent accumulator chains on the tensor pipe
+    // NS consecutive 8-row strips starting at strip tm0, all KB columns:  C -= A B^T  (strip_sub)  or
+    // A <- A Linv^T in place (strip_solve).  One warp; every tile has two accumulator chains (even / odd
+    // k-steps) and all NS * TB tiles are in flight together, because one FP64 mma costs far more latency
+    // than issue.
+    auto strip_sub = [&](auto ns_tag, double* C, const double* A, const double* B, int tm0) {
+        constexpr int NS = decltype(ns_tag)::value;
+        double af[NS][KB / 4];
+        double cc[NS][TB][2][2];
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {
+            const double* ap = A + ((tm0 + sidx) * 8 + (lane >> 2)) * KS + (lane & 3);
+#pragma unroll
+            for (int ks = 0; ks < KB / 4; ++ks) af[sidx][ks] = -ap[ks * 4];
+            const double* cp = C + ((tm0 + sidx) * 8 + (lane >> 2)) * KS + (lane & 3) * 2;
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn) {
+                const double2 c2 = *reinterpret_cast<const double2*>(cp + tn * 8);
+                cc[sidx][tn][0][0] = c2.x; cc[sidx][tn][0][1] = c2.y; cc[sidx][tn][1][0] = 0.0; cc[sidx][tn][1][1] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KB / 4; ++ks)
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn) {
+                const double bv = B[(tn * 8 + (lane >> 2)) * KS + (lane & 3) + ks * 4];
+#pragma unroll
+                for (int sidx = 0; sidx < NS; ++sidx) la_dmma(cc[sidx][tn][ks & 1][0], cc[sidx][tn][ks & 1][1], af[sidx][ks], bv);
+            }
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {
+            double* cp = C + ((tm0 + sidx) * 8 + (lane >> 2)) * KS + (lane & 3) * 2;
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn)
+                *reinterpret_cast<double2*>(cp + tn * 8) =
+                    make_double2(cc[sidx][tn][0][0] + cc[sidx][tn][1][0], cc[sidx][tn][0][1] + cc[sidx][tn][1][1]);
+        }
+    };
+    auto strip_solve = [&](auto ns_tag, double* A, const double* Lv, int tm0) {
+        constexpr int NS = decltype(ns_tag)::value;
+        double af[NS][KB / 4];
+        double cc[NS][TB][2][2];
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {
+            const double* ap = A + ((tm0 + sidx) * 8 + (lane >> 2)) * KS + (lane & 3);
+#pragma unroll
+            for (int ks = 0; ks < KB / 4; ++ks) af[sidx][ks] = ap[ks * 4];
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn) cc[sidx][tn][0][0] = cc[sidx][tn][0][1] = cc[sidx][tn][1][0] = cc[sidx][tn][1][1] = 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KB / 4; ++ks)
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn)
+                if (ks < 2 * (tn + 1)) {        // Linv is lower triangular
+                    const double bv = Lv[(tn * 8 + (lane >> 2)) * KS + (lane & 3) + ks * 4];
+#pragma unroll
+                    for (int sidx = 0; sidx < NS; ++sidx) la_dmma(cc[sidx][tn][ks & 1][0], cc[sidx][tn][ks & 1][1], af[sidx][ks], bv);
+                }
+        __syncwarp();
+#pragma unroll
+        for (int sidx = 0; sidx < NS; ++sidx) {
+            double* cp = A + ((tm0 + sidx) * 8 + (lane >> 2)) * KS + (lane & 3) * 2;
+#pragma unroll
+            for (int tn = 0; tn < TB; ++tn)
+                *reinterpret_cast<double2*>(cp + tn * 8) =
+                    make_double2(cc[sidx][tn][0][0] + cc[sidx][tn][1][0], cc[sidx][tn][0][1] + cc[sidx][tn][1][1]);
+        }
+    };
+    constexpr std::integral_constant<int, 1> one_strip{};
+    constexpr std::integral_constant<int, G::NSW> worker_strips{};
+    // b_{t+u} -= L_ut y_t for the rows of block u: thread e of `nthreads`
+    auto rhs_update = [&](int t, int u, int e) {
+        if (e < KB && t + u < T) {
+            const double* Lr = Wb + G::slot(t + u, u) * BLK + e * KS;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < KB; c += 4) {
+                s0 += Lr[c] * ycur[c]; s1 += Lr[c + 1] * ycur[c + 1];
+                s2 += Lr[c + 2] * ycur[c + 2]; s3 += Lr[c + 3] * ycur[c + 3];
+            }
+            bw[((t + u) % (Q + 1)) * KB + e] -= (s0 + s1) + (s2 + s3);
+        }
+    };
+
     while (true) {
         // ---- initial window: block rows 0..Q, then the first diagonal factor
         for (int r = 0; r <= Q && r < T; ++r) init_row(r, tid, NT);
@@ -254,80 +363,56 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         bool broke = fail_flag != 0;
         for (int t = 0; t < T && !broke; ++t) {
             const double* Lv = Li + (t & 1) * BLK;
-            // ================= B: L_ut = A_ut Linv^T (tensor pipe, one 8-row strip per job), y_t = Linv b_t
+            // ================= B (critical): L_{t+1,t} = A_{t+1,t} Linv^T on the tensor pipe, y_t = Linv b_t
+            if (t + 1 < T) {
+                double* A = Wb + G::slot(t + 1, 1) * BLK;
 #pragma unroll
-            for (int u = 1; u <= Q; ++u) {
-                if (t + u >= T) continue;
-                double* A = Wb + G::slot(t + u, u) * BLK;
-#pragma unroll
-                for (int tm = 0; tm < TB; ++tm) {
-                    if ((((u - 1) * TB + tm) % NW) != warp) continue;
-                    double af[KB / 4];
-                    const double* ap = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3);
-#pragma unroll
-                    for (int ks = 0; ks < KB / 4; ++ks) af[ks] = ap[ks * 4];
-                    double cc[TB][2];
-#pragma unroll
-                    for (int tn = 0; tn < TB; ++tn) {
-                        cc[tn][0] = cc[tn][1] = 0.0;
-                        const double* bp = Lv + (tn * 8 + (lane >> 2)) * KS + (lane & 3);
-#pragma unroll
-                        for (int ks = 0; ks < KB / 4; ++ks)
-                            if (ks < 2 * (tn + 1)) la_dmma(cc[tn][0], cc[tn][1], af[ks], bp[ks * 4]);   // Linv is lower triangular
-                    }
-                    __syncwarp();
-                    double* cp = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3) * 2;
-#pragma unroll
-                    for (int tn = 0; tn < TB; ++tn) { cp[tn * 8] = cc[tn][0]; cp[tn * 8 + 1] = cc[tn][1]; }
-                }
+                for (int tm = 0; tm < TB; ++tm)
+                    if ((tm % NW) == warp) strip_solve(one_strip, A, Lv, tm);
             }
             if (warp == NW - 1 && lane < KB) {
                 const double* bt = bw + (t % (Q + 1)) * KB;
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int k = 0; k < KB; k += 2) { s0 += Lv[lane * KS + k] * bt[k]; s1 += Lv[lane * KS + k + 1] * bt[k + 1]; }
-                const double y = s0 + s1;
+                for (int k = 0; k < KB; k += 4) {
+                    s0 += Lv[lane * KS + k] * bt[k]; s1 += Lv[lane * KS + k + 1] * bt[k + 1];
+                    s2 += Lv[lane * KS + k + 2] * bt[k + 2]; s3 += Lv[lane * KS + k + 3] * bt[k + 3];
+                }
+                const double y = (s0 + s1) + (s2 + s3);
                 ycur[lane] = y;
                 yg[t * KB + lane] = y;
             }
             __syncthreads();
             LAPROF(1);
 
-            // ================= C1: everything step t+1 waits for: D_{t+1} -= L_1t L_1t^T, b_{t+u} -= L_ut y_t
+            // ================= C1 (critical): D_{t+1} -= L_{t+1,t} L_{t+1,t}^T, b_{t+1} -= L_{t+1,t} y_t
             if (t + 1 < T) {
                 const double* A = Wb + G::slot(t + 1, 1) * BLK;
                 double* C = Wb + G::slot(t + 1, 0) * BLK;
-                int job = 0;
 #pragma unroll
                 for (int tm = 0; tm < TB; ++tm)
-#pragma unroll
-                    for (int tn = 0; tn < TB; ++tn) {
-                        if (tn > tm) continue;                    // only the lower triangle of the diagonal block is read
-                        if ((job++ % NW) != warp) continue;
-                        double* cp = C + (tm * 8 + (lane >> 2)) * KS + tn * 8 + (lane & 3) * 2;
-                        double c0 = cp[0], c1 = cp[1];
-                        const double* ap = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3);
-                        const double* bp = A + (tn * 8 + (lane >> 2)) * KS + (lane & 3);
-#pragma unroll
-                        for (int ks = 0; ks < KB / 4; ++ks) la_dmma(c0, c1, -ap[ks * 4], bp[ks * 4]);
-                        cp[0] = c0; cp[1] = c1;
-                    }
+                    if ((tm % NW) == warp) strip_sub(one_strip, C, A, A, tm);
             }
-            for (int e = tid; e < Q * KB; e += NT) {
-                const int u = 1 + e / KB, irow = e % KB;
-                if (t + u < T) {
-                    const double* Lr = Wb + G::slot(t + u, u) * BLK + irow * KS;
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < KB; c += 2) { s0 += Lr[c] * ycur[c]; s1 += Lr[c + 1] * ycur[c + 1]; }
-                    bw[((t + u) % (Q + 1)) * KB + irow] -= s0 + s1;
-                }
-            }
+            if (warp == NW - 1) rhs_update(t, 1, lane);
             __syncthreads();
             LAPROF(2);
 
-            // ================= C2: potrf of step t+1 (warp 0)  ||  rest of step t (workers)
+            // ================= C2: potrf of step t+1 (warp 0)  ||  everything else of step t (workers)
             if (warp == 0) {
+                // its share of the spill first (Linv_t and L_{t+1,t} are final since phase B), signalled to the
+                // workers, who recycle these slots for the entering row; then the look-ahead factorisation
+                double* dstg = Lg + (size_t)t * COLE;
+#pragma unroll
+                for (int ub = 0; ub <= (Q < 1 ? Q : 1); ++ub) {
+                    if (ub > 0 && t + ub >= T) continue;
+                    const double* srcb = ub == 0 ? Li + (t & 1) * BLK : Wb + G::slot(t + ub, ub) * BLK;
+                    double2* dst2 = reinterpret_cast<double2*>(dstg + ub * KK);
+                    for (int e = lane; e < KK / 2; e += 32) {
+                        const int i = e / (KB / 2), c2 = e % (KB / 2);
+                        dst2[e] = *reinterpret_cast<const double2*>(srcb + i * KS + 2 * c2);
+                    }
+                }
+                asm volatile("bar.arrive 1, %0;\n" ::"n"(NT));
                 if (t + 1 < T) potrf_inv(t + 1);
             } else {
                 const int wk = warp - 1, wt = tid - 32;
@@ -355,32 +440,50 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
                         if (wt < Kr) for (int sp = 2; sp < a.nsplit; ++sp) pfb[1] += sb[sp * a.split_stride + L + wt];
                     }
                 }
-                // (b) the trailing pairs that do not touch block column t+1's diagonal
-                int job = 0;
+#ifdef BTF_BAND_PROFILE
+                long long v0 = clock64(); wq[0] += v0 - pc0;
+#endif
+                // (a') the blocks further down: L_ut = A_ut Linv^T, u >= 2; then their right-hand sides
+                if (Q > 1) {
+                    int job = 0;
 #pragma unroll
-                for (int uu = 1; uu <= Q; ++uu) {
+                    for (int u = 2; u <= Q; ++u) {
 #pragma unroll
-                    for (int vv = 1; vv <= uu; ++vv) {
-                        if (uu == 1 && vv == 1) continue;
-                        const double* A = Wb + G::slot(t + uu, uu) * BLK;
-                        const double* B = Wb + G::slot(t + vv, vv) * BLK;
-                        double* C = Wb + G::slot(t + uu, uu - vv) * BLK;
+                        for (int tm = 0; tm < TB; tm += G::NSW) {
+                            if ((job++ % NWK) != wk) continue;
+                            if (t + u < T) strip_solve(worker_strips, Wb + G::slot(t + u, u) * BLK, Lv, tm);
+                        }
+                    }
+#ifdef BTF_BAND_PROFILE
+                    long long v1 = clock64(); wq[1] += v1 - v0; v0 = v1;
+#endif
+                    asm volatile("bar.sync 2, %0;\n" ::"n"(NWT));
+#ifdef BTF_BAND_PROFILE
+                    v1 = clock64(); wq[2] += v1 - v0; v0 = v1;
+#endif
+                }
+                // (b) the trailing pairs that do not touch the diagonal block of step t+1, by 8-row strips
+                {
+                    int job = 0;
 #pragma unroll
-                        for (int tm = 0; tm < TB; ++tm)
+                    for (int uu = 2; uu <= Q; ++uu) {
 #pragma unroll
-                            for (int tn = 0; tn < TB; ++tn) {
-                                if (uu == vv && tn > tm) continue;
+                        for (int vv = 1; vv <= uu; ++vv) {
+#pragma unroll
+                            for (int tm = 0; tm < TB; tm += G::NSW) {
                                 if ((job++ % NWK) != wk) continue;
                                 if (t + uu >= T) continue;
-                                double* cp = C + (tm * 8 + (lane >> 2)) * KS + tn * 8 + (lane & 3) * 2;
-                                double c0 = cp[0], c1 = cp[1];
-                                const double* ap = A + (tm * 8 + (lane >> 2)) * KS + (lane & 3);
-                                const double* bp = B + (tn * 8 + (lane >> 2)) * KS + (lane & 3);
-#pragma unroll
-                                for (int ks = 0; ks < KB / 4; ++ks) la_dmma(c0, c1, -ap[ks * 4], bp[ks * 4]);
-                                cp[0] = c0; cp[1] = c1;
+                                strip_sub(worker_strips, Wb + G::slot(t + uu, uu - vv) * BLK, Wb + G::slot(t + uu, uu) * BLK,
+                                          Wb + G::slot(t + vv, vv) * BLK, tm);
                             }
+                        }
                     }
+#ifdef BTF_BAND_PROFILE
+                    { long long v1 = clock64(); wq[3] += v1 - v0; }
+#endif
+#pragma unroll
+                    for (int u = 2; u <= Q; ++u)
+                        if (((u - 2) % NWK) == wk) rhs_update(t, u, lane);
                 }
 #ifdef BTF_BAND_PROFILE
                 long long w0 = clock64(); wp[0] += w0 - pc0;
@@ -389,9 +492,9 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
                 {
                     double* dstg = Lg + (size_t)t * COLE;
 #pragma unroll
-                    for (int ub = 0; ub <= Q; ++ub) {
-                        if (ub > 0 && t + ub >= T) continue;
-                        const double* srcb = ub == 0 ? Li + (t & 1) * BLK : Wb + G::slot(t + ub, ub) * BLK;
+                    for (int ub = 2; ub <= Q; ++ub) {
+                        if (t + ub >= T) continue;
+                        const double* srcb = Wb + G::slot(t + ub, ub) * BLK;
                         double2* dst2 = reinterpret_cast<double2*>(dstg + ub * KK);
                         for (int e = wt; e < KK / 2; e += NWT) {
                             const int i = e / (KB / 2), c2 = e % (KB / 2);
@@ -414,8 +517,8 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
 #ifdef BTF_BAND_PROFILE
                 long long w1 = clock64(); wp[1] += w1 - w0;
 #endif
-                // (d) the entering row reuses the slots of block column t: wait for every worker
-                asm volatile("bar.sync 1, %0;\n" ::"n"(NWT));
+                // (d) the entering row reuses the slots of block column t: wait for every worker and for warp 0's spill
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NT));
 #ifdef BTF_BAND_PROFILE
                 long long w2 = clock64(); wp[2] += w2 - w1;
 #endif
@@ -493,33 +596,29 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         if (warp < 2 && (warp == 0 || want_mean)) {
             const int rhs = warp, k = lane < KB ? lane : 0;
             double r = Lt[COLE + k] + (rhs == 0 ? zb[(t & 1) * KB + k] : 0.0);
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            // many short accumulator chains: every dependent FP64 operation costs its full latency
+            double sa[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sa[q] = 0.0;
 #pragma unroll
             for (int ub = 1; ub <= Q; ++ub) {
                 if (t + ub < T) {
                     const double* Lu = Lt + ub * KK;
                     const double* xv = xw + (rhs * (Q + 1) + (t + ub) % (Q + 1)) * KB;
 #pragma unroll
-                    for (int i = 0; i < KB; i += 4) {
-                        s0 += Lu[i * KB + k] * xv[i];
-                        s1 += Lu[(i + 1) * KB + k] * xv[i + 1];
-                        s2 += Lu[(i + 2) * KB + k] * xv[i + 2];
-                        s3 += Lu[(i + 3) * KB + k] * xv[i + 3];
-                    }
+                    for (int i = 0; i < KB; ++i) sa[i & 7] += Lu[i * KB + k] * xv[i];
                 }
             }
-            r -= (s0 + s1) + (s2 + s3);
+            r -= ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
             if (lane < KB) rb[rhs * KB + k] = r;
             __syncwarp();
             const double* rv = rb + rhs * KB;
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+            double xa[8];
 #pragma unroll
-            for (int j = 0; j < KB; j += 4) {                     // column k of Linv (zero above the diagonal)
-                x0 += Lt[j * KB + k] * rv[j];
-                x1 += Lt[(j + 1) * KB + k] * rv[j + 1];
-                x2 += Lt[(j + 2) * KB + k] * rv[j + 2];
-                x3 += Lt[(j + 3) * KB + k] * rv[j + 3];
-            }
+            for (int q = 0; q < 8; ++q) xa[q] = 0.0;
+#pragma unroll
+            for (int j = 0; j < KB; ++j) xa[j & 7] += Lt[j * KB + k] * rv[j];      // column k of Linv (zero above the diagonal)
+            const double x0 = xa[0] + xa[1], x1 = xa[2] + xa[3], x2 = xa[4] + xa[5], x3 = xa[6] + xa[7];
             const double xk = (x0 + x1) + (x2 + x3);
             if (lane < KB) {
                 xw[(rhs * (Q + 1) + t % (Q + 1)) * KB + k] = xk;
@@ -583,8 +682,11 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     LAPROF(5);
 #ifdef BTF_BAND_PROFILE
     if ((tid == 0 || tid == 32) && jl == 0)
-        printf("la T %d K %d tid %d: init %lld | B %lld | C1 %lld | C2 %lld (own %lld: prefetch+pairs %lld spill %lld bar %lld) | backward %lld | resid %lld cycles\n",
-               T, Kr, tid, pc[0], pc[1], pc[2], pc[3], pc[6], wp[0], wp[1], wp[2], pc[4], pc[5]);
+        printf("la T %d K %d tid %d: init %lld | B %lld | C1 %lld | C2 %lld (own %lld: prefetch %lld solve %lld bar2 %lld pairs %lld all-to-spill %lld spill %lld bar %lld) | backward %lld | resid %lld cycles\n",
+               T, Kr, tid, pc[0], pc[1], pc[2], pc[3], pc[6], wq[0], wq[1], wq[2], wq[3], wp[0], wp[1], wp[2], pc[4], pc[5]);
+    if ((tid == 64 || tid == 96) && jl == 0)
+        printf("la tid %d: prefetch %lld solve %lld bar2 %lld pairs %lld all-to-spill %lld spill %lld bar %lld own %lld\n",
+               tid, wq[0], wq[1], wq[2], wq[3], wp[0], wp[1], wp[2], pc[6]);
 #endif
 }
 

@@ -79,6 +79,7 @@ struct btf_engine {
     // statistics
     StatsPlan plan_row, plan_col;
     double *row_stats = nullptr, *col_stats = nullptr;
+    bool col_collapsed = false;  // split 0 of col_stats already holds the sum over splits
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
     EvalSlot eval[EVAL_SLOTS];
@@ -625,7 +626,8 @@ int btf_get_diag(btf_engine* e, const char* name, double* host, size_t n) {
         if (n != pl.out_elems_per_split) return set_err(BTF_EINVAL, "%s: expected %zu values", name, pl.out_elems_per_split);
         std::vector<double> tmp(n);
         std::fill(host, host + n, 0.0);
-        for (int s = 0; s < pl.nsplit; ++s) {
+        const int ns = (nm == "col_stats" && e->col_collapsed) ? 1 : pl.nsplit;
+        for (int s = 0; s < ns; ++s) {
             CK(cudaMemcpy(tmp.data(), src + (size_t)s * n, n * sizeof(double), cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; ++i) host[i] += tmp[i];
         }
@@ -776,6 +778,16 @@ static int enqueue_sweep(btf_engine* e) {
             if (nccl_reduce_col_stats(e->shard, e->col_stats, nsplit, e->plan_col.out_elems_per_split, e->T * e->nco, st))
                 return set_err(BTF_ENCCL, "reduce-scatter(col stats) failed");
             nsplit = 1;
+            e->col_collapsed = true;
+        } else if (nsplit > 2) {
+            // deep split-K (few columns): one pass that sums the partials in split order, instead of
+            // nsplit dependent loads per statistic inside the latency-bound band kernel
+            launch_collapse_splits(e->col_stats, nsplit, e->plan_col.out_elems_per_split, st);
+            e->launches++;
+            nsplit = 1;
+            e->col_collapsed = true;
+        } else {
+            e->col_collapsed = false;
         }
         phase_mark(e, PH_BAND_SOLVE);
         if (e->Mloc > 0) {

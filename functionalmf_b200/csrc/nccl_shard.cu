@@ -160,6 +160,10 @@ __global__ void collapse_splits_kernel(double* x, int nsplit, size_t stride) {
     }
 }
 
+void launch_collapse_splits(double* x, int nsplit, size_t stride, cudaStream_t st) {
+    if (nsplit > 1) collapse_splits_kernel<<<148 * 8, 256, 0, st>>>(x, nsplit, stride);
+}
+
 int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,
                           cudaStream_t st) {
     if (nsplit > 1) collapse_splits_kernel<<<148 * 8, 256, 0, st>>>(col_stats, nsplit, split_stride);

@@ -20,6 +20,8 @@ int nccl_allgather_rows(NcclShard* s, double* W, int K, cudaStream_t st);
 int nccl_allgather_cols(NcclShard* s, double* V, int n, cudaStream_t st);
 // in-place all-gather of a per-column vector [M]
 int nccl_allgather_doubles(NcclShard* s, double* v, cudaStream_t st);
+// x[i] += x[s * stride + i], s = 1..nsplit-1, in split order (also used on one GPU when split-K is deep)
+void launch_collapse_splits(double* x, int nsplit, size_t stride, cudaStream_t st);
 // collapse the split partials into split 0, then sum across ranks so that every rank
 // holds the totals of ITS column block (a reduce-scatter with uneven blocks)
 int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,

@@ -203,7 +203,89 @@ __global__ void __launch_bounds__(256) pg_draw_kernel(PgArgs a) {
     }
 }
 
+// Small tensors (fewer cells than the GPU has thread slots): G lanes share one cell.  A PG(b, z)
+// draw is a sum of floor(b) independent PG(1, z) draws plus a fractional term, each a long chain
+// of FP64 transcendentals, so the sum is split over the lanes (lane l takes draws l, l+G, ... and the
+// series terms k = l+1, l+1+G, ... of the fractional part, on its own Philox stream) and added up
+// with shuffles.  Same distribution as pg_draw; the streams differ from the one-thread-per-cell kernel.
+template <int G>
+__global__ void __launch_bounds__(256) pg_draw_group_kernel(PgArgs a) {
+    const long long gt = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long cell = gt / G;
+    const int l = (int)(gt % G);
+    const long long cells = (long long)a.nloc * a.P;
+    const bool in = cell < cells;
+    const int il = in ? (int)(cell / a.P) : 0, p = in ? (int)(cell - (long long)il * a.P) : 0;
+    const size_t o = (size_t)il * a.ld + p;
+    const bool obs = in && a.obs[o];
+    double acc = 0.0;
+    double b = 0.0, z = 0.0;
+    bool series = false;
+    double s = 0.0, d1 = 0.0, d2 = 0.0, bf = 0.0;
+    if (obs) {
+        const double* w = a.W + (size_t)il * a.K;
+        const double* v = a.V + (size_t)p * a.K;
+        for (int k = 0; k < a.K; ++k) z += w[k] * v[k];
+        b = a.ntr[o];
+        const bool bad = !(b > 0.0) || isinf(b) || !(z == z) || isinf(z);
+        Rng rng(a.seed, STREAM_PG + 16u * (uint32_t)(l + 1), a.scal->sweep, (uint64_t)(a.row_begin + il) * a.P + p);
+        if (bad) {
+            b = 0.0;
+        } else if (b > PG_NORMAL_B) {
+            if (l == 0) {
+                const double m = pg_mean(b, z);
+                const double vv = m + sqrt(pg_var(b, z)) * rng.normal();
+                acc = vv > 0.0 ? vv : m;
+            }
+        } else {
+            const PgTilt c = pg_setup(z);
+            const int bi = (int)floor(b);
+            bf = b - bi;
+            for (int k = l; k < bi; k += G) acc += pg_one(rng, c);
+            if (bf > 1e-12) {
+                series = true;
+                for (int k = 1 + l; k <= PG_SERIES; k += G) {
+                    const double km = k - 0.5;
+                    const double d = 4.0 * PG_PI * PG_PI * km * km + z * z;
+                    const double di = 1.0 / d;
+                    s += rng.gamma(bf) * di;
+                    d1 += di;
+                    d2 += di * di;
+                }
+            }
+        }
+    }
+    // fixed-order sums inside the lane group (groups are aligned inside the warp)
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+    }
+    if (in && l == 0) {
+        if (series) {
+            Rng rng(a.seed, STREAM_PG, a.scal->sweep, (uint64_t)(a.row_begin + il) * a.P + p);
+            const double tail_mean = pg_mean(bf, z) - 2.0 * bf * d1;
+            const double tail_var = fmax(pg_var(bf, z) - 4.0 * bf * d2, 0.0);
+            acc += 2.0 * s + fmax(tail_mean + sqrt(tail_var) * rng.normal(), 0.0);
+        }
+        a.omega[o] = obs ? acc : 0.0;
+    }
+}
+
 void launch_pg_draw(const PgArgs& a, cudaStream_t st) {
+    const long long cells = (long long)a.nloc * a.P;
+    // lane groups while the one-thread-per-cell kernel would leave most of the 148 x 2048 thread slots empty
+    int G = 1;
+    while (G < 8 && cells * (2 * G) <= (1ll << 20)) G *= 2;
+    if (G > 1) {
+        const unsigned nb = (unsigned)((cells * G + 255) / 256);
+        if (G == 2) pg_draw_group_kernel<2><<<nb, 256, 0, st>>>(a);
+        else if (G == 4) pg_draw_group_kernel<4><<<nb, 256, 0, st>>>(a);
+        else pg_draw_group_kernel<8><<<nb, 256, 0, st>>>(a);
+        return;
+    }
     dim3 grid((a.P + 255) / 256, (a.nloc + 31) / 32);
     if (a.K <= 8) pg_draw_kernel<8><<<grid, 256, 0, st>>>(a);
     else if (a.K <= 16) pg_draw_kernel<16><<<grid, 256, 0, st>>>(a);
@@ -423,19 +505,42 @@ void launch_nb_hist(const NbArgs& a, int vstride, cudaStream_t st) {
     nb_hist_kernel<<<nb, 256, 0, st>>>(a, vstride);
 }
 
+// All nmh random-walk steps of one R group in one block.  The step chain is kept as short as the
+// algorithm allows (FP64 transcendentals cost thousands of cycles of dependent latency): the
+// proposal normals and acceptance uniforms are drawn up front, one per thread; the group term
+// -n_g lgamma(r) rides along in the block sum of the histogram terms (so one lgamma deep per
+// step when the histogram fits the block); the current value's sum is carried across steps.
 __global__ void __launch_bounds__(256) nb_mh_hist_kernel(NbArgs a, int vstride) {
+    constexpr int MAXS = 256;
     __shared__ double sh[40];
+    __shared__ double zs[MAXS], us[MAXS];
     const int Rs = a.Rn * a.Rm * a.Rt;
     const int g = blockIdx.x;
     const double* hist = a.hist + (size_t)g * vstride;
     const double slog = a.work[5 * Rs + g], ng = a.work[6 * Rs + g];
     const unsigned long long sweep = a.scal->sweep;
+    auto draw_z = [&](int s) -> double {
+        if (a.z_inject) return a.z_inject[(size_t)s * Rs + g];
+        Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s) * Rs + g);
+        return rng.normal();
+    };
+    auto draw_u = [&](int s) -> double {
+        if (a.u_inject) return a.u_inject[(size_t)s * Rs + g];
+        Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s + 1) * Rs + g);
+        return rng.uniform();
+    };
+    const bool pre = a.nmh <= MAXS;
+    if (pre) {
+        for (int s = threadIdx.x; s < a.nmh; s += blockDim.x) { zs[s] = draw_z(s); us[s] = draw_u(s); }
+    }
+    // sum_v hist[v] lgamma(v + r) - n_g lgamma(r)
     auto lgsum = [&](double r) -> double {
         double acc = 0.0;
         for (int v = threadIdx.x; v < vstride; v += blockDim.x) {
             const double h = hist[v];
             if (h != 0.0) acc += h * lgamma((double)v + r);
         }
+        if (threadIdx.x == blockDim.x - 1) acc -= ng * lgamma(r);
         acc = block_sum(acc, sh);
         if (threadIdx.x == 0) sh[36] = acc;
         __syncthreads();
@@ -444,17 +549,13 @@ __global__ void __launch_bounds__(256) nb_mh_hist_kernel(NbArgs a, int vstride) 
     double R = a.Rdisp[g], logR = log(R);
     double lg_cur = lgsum(R);
     for (int s = 0; s < a.nmh; ++s) {
-        double z;
-        if (a.z_inject) z = a.z_inject[(size_t)s * Rs + g];
-        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s) * Rs + g); z = rng.normal(); }
+        const double z = pre ? zs[s] : draw_z(s);
         const double lc = logR + a.rpropstdev * z, Rc = exp(lc);
         const double lg_cand = lgsum(Rc);
         const double dprior = -(lc * lc - logR * logR) / (2.0 * a.rstdev * a.rstdev);
-        const double ll = lg_cand - lg_cur - ng * (lgamma(Rc) - lgamma(R)) + (Rc - R) * slog;
+        const double ll = lg_cand - lg_cur + (Rc - R) * slog;
         const double prob = exp(clampd(dprior + ll, -10.0, 1.0));
-        double u;
-        if (a.u_inject) u = a.u_inject[(size_t)s * Rs + g];
-        else { Rng rng(a.seed, STREAM_R, sweep, (uint64_t)(2 * s + 1) * Rs + g); u = rng.uniform(); }
+        const double u = pre ? us[s] : draw_u(s);
         if (u <= prob && Rc > 1.0) { R = Rc; logR = lc; lg_cur = lg_cand; }     // block-uniform
     }
     if (threadIdx.x == 0) a.Rdisp[g] = R;
