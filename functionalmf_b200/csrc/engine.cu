@@ -80,6 +80,10 @@ struct btf_engine {
     StatsPlan plan_row, plan_col;
     double *row_stats = nullptr, *col_stats = nullptr;
     bool col_collapsed = false;  // split 0 of col_stats already holds the sum over splits
+    // K1 on the integer tensor cores (stats_i8.cu): decided per data set, buffers allocated on first use
+    bool i8_on = false, i8_decided = false;
+    StatsI8Buffers i8{};
+    uint8_t* cntT = nullptr;     // [P][nloc_pad] transposed counts (right operand of the column contraction)
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
     EvalSlot eval[EVAL_SLOTS];
@@ -327,6 +331,10 @@ void btf_destroy(btf_engine* e) {
                     e->row_stats, e->col_stats, e->zbuf, e->mu_mean, e->mu_m2, e->work_L, e->work_y, e->partials, e->lam_partials, e->resid_partials,
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
+    {
+        void* i8p[] = {e->i8.planes, e->i8.colmax, e->i8.expo, e->i8.D, e->i8.bpart, e->cntT};
+        for (void* q : i8p) if (q) cudaFree(q);
+    }
     for (int i = 0; i < EVAL_SLOTS; ++i) eval_free(e->eval[i]);
     for (auto& kv : e->inject) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& kv : e->diagbuf) if (kv.second.p) cudaFree(kv.second.p);
@@ -393,7 +401,7 @@ int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int
     CK(cudaStreamSynchronize(e->stream));
     if (staging) CK(cudaFree(staging));
     CK(cudaGetLastError());
-    e->has_data = true; e->data_reduced = false; e->resid_valid = false;
+    e->has_data = true; e->data_reduced = false; e->resid_valid = false; e->i8_decided = false;
     return BTF_OK;
 }
 
@@ -432,7 +440,7 @@ int btf_set_data_binomial(btf_engine* e, const double* Ys, const double* Nt) {
     if (sy) CK(cudaFree(sy));
     if (sn) CK(cudaFree(sn));
     CK(cudaGetLastError());
-    e->has_data = true; e->data_reduced = true;
+    e->has_data = true; e->data_reduced = true; e->i8_decided = false;
     return BTF_OK;
 }
 
@@ -474,7 +482,7 @@ int btf_set_data_negbin(btf_engine* e, const double* Y, int32_t nreps) {
             e->launches += 2;
         }
     }
-    e->has_data = true; e->data_reduced = true;
+    e->has_data = true; e->data_reduced = true; e->i8_decided = false;
     return BTF_OK;
 }
 
@@ -626,7 +634,7 @@ int btf_get_diag(btf_engine* e, const char* name, double* host, size_t n) {
         if (n != pl.out_elems_per_split) return set_err(BTF_EINVAL, "%s: expected %zu values", name, pl.out_elems_per_split);
         std::vector<double> tmp(n);
         std::fill(host, host + n, 0.0);
-        const int ns = (nm == "col_stats" && e->col_collapsed) ? 1 : pl.nsplit;
+        const int ns = (e->i8_on || (nm == "col_stats" && e->col_collapsed)) ? 1 : pl.nsplit;
         for (int s = 0; s < ns; ++s) {
             CK(cudaMemcpy(tmp.data(), src + (size_t)s * n, n * sizeof(double), cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; ++i) host[i] += tmp[i];
@@ -652,7 +660,44 @@ static inline void phase_mark(btf_engine* e, int idx) {
     if (e->time_phases) cudaEventRecord(e->ph_ev[idx], e->stream);
 }
 
+// The integer-tensor-core statistics path: Gaussian data (count weights), K in {8, 16, 32}, accumulators
+// that cannot overflow, and a tensor large enough for the digit planes to pay (BTF_STATS_FORCE_I8=1
+// forces it for any size, BTF_STATS_NO_I8=1 disables it).
+static int ensure_i8(btf_engine* e) {
+    if (e->i8_decided) return BTF_OK;
+    e->i8_decided = true;
+    e->i8_on = false;
+    if (e->cfg.likelihood != BTF_GAUSSIAN || !e->has_data) return BTF_OK;
+    static const bool force = getenv("BTF_STATS_FORCE_I8") != nullptr;
+    const long long cells = (long long)e->nloc * e->P;
+    if (!stats_i8_supported(e->K, e->nreps, e->Ppad, e->nloc_pad) || e->nloc < 1) return BTF_OK;
+    if (!force && cells < (1ll << 24)) return BTF_OK;
+    if (!e->i8.planes) {
+        StatsI8Sizes z;
+        stats_i8_sizes(e->K, e->nloc_pad, e->Ppad, e->nloc, e->P, &z);
+        CK(cudaMalloc((void**)&e->i8.planes, z.planes_bytes));
+        CK(cudaMemset(e->i8.planes, 0, z.planes_bytes));
+        CK(dev_alloc(&e->i8.colmax, (size_t)z.L));
+        CK(dev_alloc(&e->i8.expo, (size_t)z.L));
+        CK(dev_alloc(&e->i8.D, z.d_elems, false));
+        CK(dev_alloc(&e->i8.bpart, z.bpart_elems));
+        CK(dev_alloc(&e->cntT, z.cntT_bytes));
+        e->i8.nsplit_b_row = z.nsplit_b_row;
+    }
+    launch_transpose_u8(e->cnt, e->Ppad, e->nloc, e->P, e->cntT, e->nloc_pad, e->stream);
+    e->launches++;
+    // one eager pass so that every kernel attribute is set before a graph capture
+    if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
+                        e->row_stats, e->stream))
+        return set_err(BTF_ECUDA, "integer statistics path failed to launch");
+    CK(cudaStreamSynchronize(e->stream));
+    e->i8_on = true;
+    free_graph(e);
+    return BTF_OK;
+}
+
 static int ensure_data_reduced(btf_engine* e) {
+    { int rc = ensure_i8(e); if (rc) return rc; }
     if (e->data_reduced) return BTF_OK;
     if (e->shard) {
         int rc = nccl_allreduce_sum(e->shard, &e->scal->ss_total, 2, e->stream);   // ss_total, n_obs adjacent
@@ -745,11 +790,18 @@ static int enqueue_sweep(btf_engine* e) {
     phase_mark(e, PH_ROW_STATS);
     const void* wt = gauss ? (const void*)e->cnt : (const void*)e->omega;
     if ((mask & BTF_SAMPLE_W) && e->nloc > 0) {
-        launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->Ppad, e->nloc, e->row_stats, e->zbuf, st);
-        e->launches += e->plan_row.zpre ? 2 : 1;
+        if (e->i8_on) {
+            if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
+                                e->row_stats, st))
+                return set_err(BTF_ECUDA, "integer row statistics failed to launch");
+            e->launches += 5;
+        } else {
+            launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->Ppad, e->nloc, e->row_stats, e->zbuf, st);
+            e->launches += e->plan_row.zpre ? 2 : 1;
+        }
         phase_mark(e, PH_ROW_SOLVE);
         RowSolveArgs ra;
-        ra.stats = e->row_stats; ra.nsplit = e->plan_row.nsplit; ra.split_stride = e->plan_row.out_elems_per_split;
+        ra.stats = e->row_stats; ra.nsplit = e->i8_on ? 1 : e->plan_row.nsplit; ra.split_stride = e->plan_row.out_elems_per_split;
         ra.nloc = e->nloc; ra.row_begin = c.row_begin; ra.K = e->K;
         ra.scale_from_nu2 = gauss ? &e->scal->nu2 : nullptr; ra.scal = e->scal; ra.W = e->W;
         ra.z_inject = inj(e, "z_W"); ra.seed = c.seed;
@@ -768,10 +820,18 @@ static int enqueue_sweep(btf_engine* e) {
     }
     // ---- V | rest
     if (mask & BTF_SAMPLE_V) {
-        launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->nloc_pad, e->Ppad, e->P,
-                     e->col_stats, e->zbuf, st);
-        e->launches += e->plan_col.zpre ? 2 : 1;
         int nsplit = e->plan_col.nsplit;
+        if (e->i8_on) {
+            if (launch_stats_i8(e->i8, true, e->K, e->cntT, e->nloc_pad, e->S, e->Ppad, e->W + (size_t)c.row_begin * e->K,
+                                e->nloc, e->nloc_pad, e->P, e->Ppad, e->col_stats, st))
+                return set_err(BTF_ECUDA, "integer column statistics failed to launch");
+            e->launches += 5;
+            nsplit = 1;
+        } else {
+            launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->nloc_pad, e->Ppad, e->P,
+                         e->col_stats, e->zbuf, st);
+            e->launches += e->plan_col.zpre ? 2 : 1;
+        }
         if (e->shard) {
             // sum the split partials locally is folded into the band kernel only on one GPU; across GPUs the
             // partial statistics are first collapsed over splits, then reduce-scattered by column block

@@ -42,6 +42,24 @@ bool plan_stats_zpre(StatsPlan* p, bool trans, bool weights_f64, int mdim_pad, i
 void launch_stats_zpre(const StatsPlan& p, bool trans, const void* wt, const double* sv, const double* F,
                        long long frows, long long ld, int m_valid, double* out, double* Zg, cudaStream_t st);
 
+// ---------------------------------------------------------------- K1 on the integer tensor cores (stats_i8.cu, i8gemm.cu)
+struct StatsI8Sizes { size_t planes_bytes, d_elems, cntT_bytes, bpart_elems; int nsplit_b_row, L; };
+struct StatsI8Buffers {
+    int8_t* planes;                 // [8 L][kdim_pad] signed base-128 digits of Z
+    unsigned long long* colmax;     // [L] max |Z| per column (bit pattern)
+    int* expo;                      // [L] column exponents
+    int32_t* D;                     // [8 L][m_pad] exact digit-plane contractions
+    double* bpart;                  // [nsplit][m][K] partial sums of the linear block
+    int nsplit_b_row;
+};
+bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col);
+void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes* s);
+void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, uint8_t* dst, long long ldd, cudaStream_t st);
+// out[m][L+K] (one split) for count weights: exact product block + FP64 linear block
+int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
+                    long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,
+                    cudaStream_t st);
+
 // ---------------------------------------------------------------- residual (nu2)
 // resid_partials[b] = sum over the block's cells of cnt*Mu^2 - 2*Mu*S
 void launch_residual(const uint8_t* cnt, const double* S, long long ld, const double* W, const double* V,

@@ -1,0 +1,293 @@
+// K1 on the integer tensor cores: the Gaussian sufficient statistics with count weights,
+//   out[m, c] = sum_k cnt[m, k] Z[k, c]   (c < L: packed products F[k,k1] F[k,k2]),   out[m, L + j] = sum_k S[m, k] F[k, j],
+// computed EXACTLY for the product block and in FP64 for the (small) linear block.
+//
+// The left operand of the product block is an integer (cnt = number of observed replicates), so every
+// column of Z is written as a fixed-point number against a power-of-two column scale,
+//   Z[k, c] ~ 2^(e_c - 54) q[k, c],   q = round(Z 2^(54 - e_c)),  |q| <= 2^54,   q = sum_{s<8} 128^s d_s,  d_s in [-64, 63],
+// and the eight digit planes are contracted with the counts by ONE exact int8 x int8 -> int32 GEMM on the
+// tcgen05 tensor cores (i8gemm.cu):  D[(s, c), m] = sum_k d_s[k, c] cnt[m, k].  The planes are recombined in
+// integer arithmetic ((D7..D4) and (D3..D0) as two int64 Horner sums, each exactly representable in a
+// double) and rounded once.  The only error is the 2^-55 (relative to the column maximum) rounding of Z
+// itself - below the rounding noise of an FP64 accumulation over the same number of terms - and the result
+// does not depend on the order of summation at all.
+// Replaces the DMMA kernel for the product block (L of the L + K columns: 89 % of the flops at K = 16);
+// the linear block stays on the FP64 pipe (sf_kernel, HBM bound: it has to read S once).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "kernels.h"
+#include "stats_common.cuh"
+
+namespace btf {
+
+int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
+                  long long ldd, cudaStream_t st);
+
+namespace {
+
+constexpr int NPLANES = 8;
+constexpr int FIXBITS = 54;
+
+__device__ __forceinline__ void pair_of(int c, int& k1, int& k2) {
+    k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
+    while (k1 * (k1 + 1) / 2 > c) --k1;
+    while ((k1 + 1) * (k1 + 2) / 2 <= c) ++k1;
+    k2 = c - k1 * (k1 + 1) / 2;
+}
+
+// colmax[c] = max_r |F[r,k1] F[r,k2]| (bit pattern of a non-negative double, so an integer max is exact)
+__global__ void __launch_bounds__(256) zmax_kernel(const double* __restrict__ F, int rows, int K, int L,
+                                                   unsigned long long* __restrict__ colmax) {
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    int k1 = 0, k2 = 0;
+    if (c < L) pair_of(c, k1, k2);
+    double m = 0.0;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* fr = F + (long long)r * K;
+        if (c < L) m = fmax(m, fabs(fr[k1] * fr[k2]));
+    }
+    if (c < L && m > 0.0) atomicMax(colmax + c, (unsigned long long)__double_as_longlong(m));
+}
+
+// digit planes: planes[(s L + c) ldk + r] = d_s of q[r, c].  A block stages 256 rows of F in shared memory;
+// thread (tx, ty): rows 4 tx .. 4 tx + 3 (one 4-byte store per plane), columns c = ty, ty + 4, ...
+__global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ F, int rows, int rows_pad, int K, int L,
+                                                      const unsigned long long* __restrict__ colmax,
+                                                      int* __restrict__ expo, int8_t* __restrict__ planes, long long ldk) {
+    extern __shared__ __align__(16) double zsm[];
+    const int KS = K + 1;
+    double* Fs = zsm;                                              // [256][K + 1]
+    unsigned short* pairs = reinterpret_cast<unsigned short*>(Fs + 256 * KS);   // [L]  (k1 << 8 | k2)
+    const int rb = blockIdx.x * 256;
+    for (int e = threadIdx.x; e < 256 * K; e += 256) {
+        const int r = e / K, k = e - r * K;
+        Fs[r * KS + k] = (rb + r < rows) ? F[(long long)(rb + r) * K + k] : 0.0;
+    }
+    for (int c = threadIdx.x; c < L; c += 256) {
+        int k1, k2;
+        pair_of(c, k1, k2);
+        pairs[c] = (unsigned short)((k1 << 8) | k2);
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int r0 = rb + 4 * tx;
+    if (r0 >= rows_pad) return;
+    for (int c = ty; c < L; c += 4) {
+        const int k1 = pairs[c] >> 8, k2 = pairs[c] & 0xff;
+        const double mx = __longlong_as_double((long long)colmax[c]);
+        const int e = mx > 0.0 ? ilogb(mx) + 1 : 0;                // max < 2^e
+        if (r0 == 0) expo[c] = e;
+        unsigned dig[NPLANES];
+#pragma unroll
+        for (int s = 0; s < NPLANES; ++s) dig[s] = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double* fr = Fs + (4 * tx + u) * KS;
+            long long q = __double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e));
+#pragma unroll
+            for (int s = 0; s < NPLANES; ++s) {
+                const long long d = ((q + 64) & 127) - 64;          // signed digit in [-64, 63]
+                q = (q - d) >> 7;
+                dig[s] |= ((unsigned)(d & 0xff)) << (8 * u);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NPLANES; ++s)
+            *reinterpret_cast<unsigned*>(planes + ((long long)s * L + c) * ldk + r0) = dig[s];
+    }
+}
+
+// out[split][m][j] = sum_k S[m,k] F[k,j] over the split's k range: FP64 tensor pipe, HBM bound
+template <int KB, bool TRANS>
+__global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ F,
+                                                    int K, int m_valid, int nchunks, int chunks_per_split,
+                                                    double* __restrict__ out) {
+    constexpr int BM = 64, KC = 64, SS = 68, FS = KB + 4, CT = KB / 8;
+    extern __shared__ __align__(16) double smf[];
+    double* Ssm = smf;                       // [2][64][SS]   (!TRANS: [m][k], TRANS: [k][m])
+    double* Fsm = smf + 2 * 64 * SS;         // [2][KC][FS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * BM;
+    const int c_begin = blockIdx.y * chunks_per_split, c_end = min(nchunks, c_begin + chunks_per_split);
+    auto load = [&](int stage, int chunk) {
+        const long long k0 = (long long)chunk * KC;
+        double* sd = Ssm + stage * 64 * SS;
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, q = e & 31;
+            const double* src = TRANS ? S + (k0 + r) * lds + m0 + 2 * q : S + (long long)(m0 + r) * lds + k0 + 2 * q;
+            cp_async16(sd + r * SS + 2 * q, src);
+        }
+        double* fd = Fsm + stage * KC * FS;
+        for (int e = tid; e < KC * K / 2; e += 256) {
+            const int r = (2 * e) / K, cidx = (2 * e) - r * K;
+            cp_async16(fd + r * FS + cidx, F + (k0 + r) * K + cidx);
+        }
+    };
+    double acc[CT][2];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c][0] = acc[c][1] = 0.0;
+    // zero the padding columns of the F tiles once (K < KB)
+    for (int e = tid; e < 2 * KC * FS; e += 256) Fsm[e] = 0.0;
+    __syncthreads();
+    if (c_begin < c_end) load(0, c_begin);
+    cp_async_commit();
+    for (int c = c_begin; c < c_end; ++c) {
+        const int stg = (c - c_begin) & 1;
+        if (c + 1 < c_end) load(stg ^ 1, c + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* sd = Ssm + stg * 64 * SS;
+        const double* fd = Fsm + stg * KC * FS;
+        const int ml = warp * 8 + (lane >> 2);
+#pragma unroll 4
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            const int kl = kk * 4 + (lane & 3);
+            const double av = TRANS ? sd[kl * SS + ml] : sd[ml * SS + kl];
+#pragma unroll
+            for (int ct = 0; ct < CT; ++ct) dmma(acc[ct][0], acc[ct][1], av, fd[kl * FS + ct * 8 + (lane >> 2)]);
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    const int m = m0 + warp * 8 + (lane >> 2);
+    if (m < m_valid) {
+        double* o = out + ((long long)blockIdx.y * m_valid + m) * K;
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = ct * 8 + (lane & 3) * 2 + h;
+                if (j < K) o[j] = acc[ct][h];
+            }
+    }
+}
+
+// out[m][c] = 2^(e_c - 54) sum_s 128^s D[(s L + c) ldn + m]  (32 x 32 tiles through shared memory),
+// out[m][L + j] = sum_split bpart[split][m][j]
+__global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restrict__ D, long long ldn, const int* __restrict__ expo,
+                                                         const double* __restrict__ bpart, int nsplit_b, int m_valid, int L,
+                                                         int K, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int nco = L + K;
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    if (c0 < L) {
+        for (int cy = ty; cy < 32; cy += 8) {
+            const int c = c0 + cy, m = m0 + tx;
+            double v = 0.0;
+            if (c < L && m < m_valid) {
+                const int32_t* d = D + (long long)c * ldn + m;
+                const long long pl = (long long)L * ldn;
+                long long hi = d[7 * pl], lo = d[3 * pl];
+                hi = hi * 128 + d[6 * pl]; lo = lo * 128 + d[2 * pl];
+                hi = hi * 128 + d[5 * pl]; lo = lo * 128 + d[1 * pl];
+                hi = hi * 128 + d[4 * pl]; lo = lo * 128 + d[0];
+                v = scalbn(fma((double)hi, 268435456.0, (double)lo), expo[c] - FIXBITS);
+            }
+            tile[cy][tx] = v;
+        }
+        __syncthreads();
+        for (int my = ty; my < 32; my += 8) {
+            const int m = m0 + my, c = c0 + tx;
+            if (m < m_valid && c < L) out[(long long)m * nco + c] = tile[tx][my];
+        }
+    } else {
+        // the linear block: columns L .. L+K-1 (this block row handles all of them for its 32 rows)
+        for (int e = threadIdx.x; e < 32 * K; e += 256) {
+            const int m = m0 + e / K, j = e % K;
+            if (m < m_valid) {
+                double s = 0.0;
+                for (int sp = 0; sp < nsplit_b; ++sp) s += bpart[((long long)sp * m_valid + m) * K + j];
+                out[(long long)m * nco + L + j] = s;
+            }
+        }
+    }
+}
+
+// dst[p][i] = src[i][p]  (uint8), 32 x 32 tiles
+__global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t* __restrict__ src, long long lds, int rows, int cols,
+                                                           uint8_t* __restrict__ dst, long long ldd) {
+    __shared__ uint8_t tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int y = ty; y < 32; y += 8) {
+        const int r = r0 + y, c = c0 + tx;
+        tile[y][tx] = (r < rows && c < cols) ? src[(long long)r * lds + c] : (uint8_t)0;
+    }
+    __syncthreads();
+    for (int y = ty; y < 32; y += 8) {
+        const int c = c0 + y, r = r0 + tx;
+        if (c < cols && r < rows) dst[(long long)c * ldd + r] = tile[tx][y];
+    }
+}
+
+template <int KB, bool TRANS>
+void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks,
+                 int nsplit, double* out, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * 64 * 68 + 2 * 64 * (KB + 4)) * sizeof(double);
+    auto kern = sf_kernel<KB, TRANS>;
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+    const int cps = (nchunks + nsplit - 1) / nsplit;
+    kern<<<dim3(m_tiles, nsplit), 256, smem, st>>>(S, lds, F, K, m_valid, nchunks, cps, out);
+}
+
+}  // namespace
+
+bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col) {
+    static const bool off = getenv("BTF_STATS_NO_I8") != nullptr;
+    if (off) return false;
+    if (!(K == 8 || K == 16 || K == 32)) return false;
+    if (nreps < 1 || nreps > 127) return false;
+    const long long kd = kdim_row > kdim_col ? kdim_row : kdim_col;
+    return kd * nreps * 64 < (1ll << 31);           // the int32 accumulators cannot overflow
+}
+
+void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes* s) {
+    const long long L = (long long)K * (K + 1) / 2;
+    const long long kd = std::max(nloc_pad, Ppad), nd = std::max(nloc_pad, Ppad);
+    s->planes_bytes = (size_t)(NPLANES * L * kd);
+    s->d_elems = (size_t)(NPLANES * L * nd);
+    s->cntT_bytes = (size_t)P * nloc_pad;
+    s->nsplit_b_row = 4;
+    s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)P * K);
+    s->L = (int)L;
+}
+
+void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, uint8_t* dst, long long ldd, cudaStream_t st) {
+    transpose_u8_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+}
+
+// trans = false: m = local row, contraction over p (B = cnt [nloc][ldb = Ppad], F = V [P][K], S [nloc_pad][lds])
+// trans = true : m = p, contraction over local rows (B = cntT [P][ldb = nloc_pad], F = W local [nloc][K], S the same array)
+int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
+                    long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,
+                    cudaStream_t st) {
+    const int L = K * (K + 1) / 2;
+    const long long ldk = kdim_pad, ldn = m_pad;
+    // 1. column scales and digit planes of Z
+    cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
+    zmax_kernel<<<dim3(148 * 4, (L + 255) / 256), 256, 0, st>>>(F, f_rows, K, L, w.colmax);
+    {
+        const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
+        static size_t zs_set = 0;
+        if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
+        zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, ldk);
+    }
+    // 2. exact product block on the tensor cores
+    if (launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st)) return 1;
+    // 3. linear block in FP64
+    const int nchunks = kdim_pad / 64;
+    const int nsplit = trans ? 1 : w.nsplit_b_row;
+    const int m_tiles = (m_valid + 63) / 64;
+    if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
+    else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
+    else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
+    // 4. recombination
+    i8_combine_kernel<<<dim3((m_valid + 31) / 32, (L + 31) / 32 + 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+}  // namespace btf

@@ -176,6 +176,11 @@ double btf_hbm_copy_gbs(int32_t device, size_t bytes, int32_t iters);
 int btf_pg_sample(int32_t device, const double* b, const double* z, double* out, int64_t n, uint64_t seed);
 int btf_rng_sample(int32_t device, int32_t kind, double param, double* out, int64_t n, uint64_t seed);
 
+/* Exact int8 x int8 -> int32 GEMM on the tcgen05 tensor cores (test / benchmark hook of the digit-plane
+ * statistics path): D[M, N] = A[M, K] . B[N, K]^T, host buffers, K a multiple of 128.  Returns the time of
+ * `reps` launches in ms, negative on failure. */
+double btf_i8gemm_test(int32_t device, const int8_t* A, const int8_t* B, int32_t* D, int32_t M, int32_t N, int32_t K,
+                       int32_t reps);
 /* ---- NCCL plumbing for the sharded sweep */
 int btf_nccl_unique_id(char* id128);                    /* 128-byte ncclUniqueId */
 int btf_nccl_init(btf_engine* e, const char* id128);    /* uses cfg.world_size / cfg.rank */
