@@ -11,9 +11,12 @@ configs[1] ("c2": 4096 x 1024 x 64 x 3 replicates, nembeds=16, tf_order=2, 20 % 
   engine's stream (inputs 2.4 GB >> 126 MB L2, so no L2 flush is needed).
 * ``e2e``    : the same metric through the public ``run_gibbs`` path from HOST buffers:
   upload of Y, pre-reduction, K sweeps, device->host copy of every saved sample.
-* ``roofline``: the two statistics contractions (FP64 DMMA), algorithmic flops / measured
-  kernel time against the FP64 peak measured by the library's own micro-benchmark
-  (MEASURED_PEAKS.json has no FP64 entry).
+* ``roofline``: the dominant kernel of the sweep.  With the integer-tensor-core statistics path
+  (stats_i8.cu, the default for Gaussian data at this size) that is ``i8gemm_kernel`` (tcgen05 int8):
+  executed int8 operations / its CUDA-event time against twice the measured dense bf16 rate of
+  MEASURED_PEAKS.json, with the FP64-equivalent rate of the product block and the HBM rate of the FP64
+  linear block beside it; with ``BTF_STATS_NO_I8=1`` the FP64 DMMA kernels against the FP64 peak measured
+  by the library's own micro-benchmark (MEASURED_PEAKS.json has no FP64 entry).
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the reference path
   (oracle/btf_oracle.py) timed on a bounded sample of the same workload and
   extrapolated linearly in rows / columns (stated in ``sample``).
@@ -30,6 +33,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of i8gemm_kernel (mean of the row and the column launch)
+# from the ncu --set full capture of the same command (profiles/); None until captured
+I8_TRAFFIC = {}
 
 WORKLOADS = {
     # name: N, M, T, R, K, order, nan_frac
@@ -369,6 +376,52 @@ def bench_ours(args):
         # workload (profiles/r1_ncu_stats_zpre_summary.txt: rows 2.504 GB read + 0.029 GB written,
         # columns 2.436 GB + 0.144 GB); algorithmic bytes per launch are cells * 9 B = 2.416 GB
         traffic = 2.5566e9 if (args.workload == 'c2' and world == 1) else None
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
+                    'kernel': 'stats_kernel (row + column sufficient-statistic contractions, FP64 DMMA)',
+                    'flops_per_sweep_per_gpu': flops_stats, 'kernel_ms_per_sweep': stats_ms,
+                    'peak_source': 'btf_fp64_peak micro-benchmark in this run (DMMA %.2f, DFMA %.2f TFLOP/s); '
+                                   'MEASURED_PEAKS.json has no FP64 entry' % (dmma, dfma),
+                    'hbm': {'achieved': bytes_stats / (stats_ms * 1e-3) / 1e9 if stats_ms > 0 else None,
+                            'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src,
+                            'bytes_per_sweep_per_gpu': bytes_stats}}
+        gemm_ms = phases.get('row_i8gemm', 0.0) + phases.get('col_i8gemm', 0.0)
+        if gemm_ms > 0:
+            # integer-tensor-core path (stats_i8.cu): the dominant kernel is i8gemm_kernel, two launches per
+            # sweep.  Executed work: 8 digit planes x L product columns against the counts,
+            # 2 * (8 L) * rows * (padded contraction length) int8 operations per launch.
+            nloc, nloc_pad = eng.nloc, -(-eng.nloc // 128) * 128
+            P, Ppad = M * T, -(-(M * T) // 256) * 256
+            ops = 2.0 * (8 * Lp) * (float(nloc) * Ppad + float(P) * nloc_pad)
+            bf16 = None
+            if os.path.exists(peaks_file):
+                try:
+                    bf16 = json.load(open(peaks_file)).get('bf16_tflops')
+                except Exception:
+                    bf16 = None
+            i8_peak = 2.0 * (bf16 or 1634.5)
+            ach = ops / (gemm_ms * 1e-3) / 1e12
+            lin_ms = phases.get('row_linear', 0.0) + phases.get('col_linear', 0.0)
+            roofline = {
+                'bound': 'tensor', 'achieved': ach, 'peak': i8_peak, 'unit': 'TFLOP/s', 'frac': ach / i8_peak,
+                'traffic': I8_TRAFFIC.get((args.workload, world)),
+                'kernel': 'i8gemm_kernel (tcgen05.mma.kind::i8: exact digit-plane contraction of the product block '
+                          'of the row and the column statistics; int8 operations counted as executed)',
+                'ops_per_sweep_per_gpu': ops, 'kernel_ms_per_sweep': gemm_ms,
+                'peak_source': '2 x the measured dense bf16 rate of MEASURED_PEAKS.json (%s TFLOP/s burst; the int8 '
+                               'tensor rate of this part is twice its bf16 rate); no int8 entry there' % (bf16 or 'fallback 1634.5'),
+                'algorithmic_fp64': {
+                    'flops_per_sweep_per_gpu': 4.0 * cells * Lp / world,
+                    'tflops_at_gemm_time': 4.0 * cells * Lp / world / (gemm_ms * 1e-3) / 1e12,
+                    'fp64_dmma_peak': dmma,
+                    'note': 'FP64 flops of the product block (SURVEY 8d) divided by the int8 GEMM time: what the exact '
+                            'fixed-point formulation delivers against the FP64 pipe it replaces'},
+                'linear_block': {'kernel': 'sf_kernel (FP64 DMMA, reads S once per contraction)',
+                                 'ms_per_sweep': lin_ms, 'bytes_per_sweep_per_gpu': 2.0 * cells * 8.0 / world,
+                                 'achieved_gbs': 2.0 * cells * 8.0 / world / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None,
+                                 'peak_gbs': hbm_peak, 'peak_source': hbm_src},
+                'statistics_ms_per_sweep': stats_ms,
+            }
         out = {
             'metric': 'Gibbs sweeps/sec', 'value': args.steps / (ms * 1e-3), 'unit': 'sweeps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
@@ -381,15 +434,7 @@ def bench_ours(args):
             'e2e': e2e,
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
-                         'kernel': 'stats_kernel (row + column sufficient-statistic contractions, FP64 DMMA)',
-                         'flops_per_sweep_per_gpu': flops_stats, 'kernel_ms_per_sweep': stats_ms,
-                         'peak_source': 'btf_fp64_peak micro-benchmark in this run (DMMA %.2f, DFMA %.2f TFLOP/s); '
-                                        'MEASURED_PEAKS.json has no FP64 entry' % (dmma, dfma),
-                         'hbm': {'achieved': bytes_stats / (stats_ms * 1e-3) / 1e9 if stats_ms > 0 else None,
-                                 'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src,
-                                 'bytes_per_sweep_per_gpu': bytes_stats}},
+            'roofline': roofline,
             'phases_ms': phases,
             'state': st_final,
             'e2e_gpu_launches': int(e2e_launches),

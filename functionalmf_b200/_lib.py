@@ -15,7 +15,9 @@ GAUSSIAN, BINOMIAL, NEGBINOMIAL = 0, 1, 2
 SAMPLE_NU2, SAMPLE_SIGMA2, SAMPLE_TAU2, SAMPLE_LAM2, SAMPLE_W, SAMPLE_V, SAMPLE_R = 1, 2, 4, 8, 16, 32, 64
 SAMPLE_ALL = 127
 INIT_SIGMA2, INIT_LAM2, INIT_NU2, INIT_TAU2, INIT_W, INIT_V, INIT_R = 1, 2, 4, 8, 16, 32, 64
-PHASES = ['nu2_or_pg', 'sigma2', 'tau2', 'lam2', 'row_stats', 'row_solve', 'col_stats', 'band_solve', 'comm']
+PHASES = ['nu2_or_pg', 'sigma2', 'tau2', 'lam2', 'row_stats', 'row_solve', 'col_stats', 'band_solve', 'comm',
+          # sub-phases of row_stats / col_stats on the integer-tensor-core path (0 when it is off)
+          'row_i8gemm', 'row_linear', 'col_i8gemm', 'col_linear']
 
 
 class BTFLibraryError(RuntimeError):

@@ -107,6 +107,7 @@ struct btf_engine {
     // phase timing
     bool time_phases = false;
     cudaEvent_t ph_ev[PH_COUNT + 1] = {nullptr};
+    cudaEvent_t i8_ev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [row|col][before gemm, after gemm, after linear]
     double ph_ms[PH_COUNT] = {0};
     // multi GPU
     NcclShard* shard = nullptr;
@@ -206,6 +207,7 @@ int btf_create(const btf_config* c, btf_engine** out) {
     CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&e->ph_ev[i]));
+    for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&e->i8_ev[i / 3][i % 3]));
 
     e->delta = build_delta(e->T, e->order, &e->RD);
     const int RD = e->RD, T = e->T, q = e->q;
@@ -342,6 +344,7 @@ void btf_destroy(btf_engine* e) {
     if (e->ev_snap) cudaEventDestroy(e->ev_snap);
     if (e->ev_copied) cudaEventDestroy(e->ev_copied);
     for (int i = 0; i <= PH_COUNT; ++i) if (e->ph_ev[i]) cudaEventDestroy(e->ph_ev[i]);
+    for (int i = 0; i < 6; ++i) if (e->i8_ev[i / 3][i % 3]) cudaEventDestroy(e->i8_ev[i / 3][i % 3]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -668,7 +671,7 @@ static int ensure_i8(btf_engine* e) {
     e->i8_decided = true;
     e->i8_on = false;
     if (e->cfg.likelihood != BTF_GAUSSIAN || !e->has_data) return BTF_OK;
-    static const bool force = getenv("BTF_STATS_FORCE_I8") != nullptr;
+    const bool force = getenv("BTF_STATS_FORCE_I8") != nullptr;
     const long long cells = (long long)e->nloc * e->P;
     if (!stats_i8_supported(e->K, e->nreps, e->Ppad, e->nloc_pad) || e->nloc < 1) return BTF_OK;
     if (!force && cells < (1ll << 24)) return BTF_OK;
@@ -791,6 +794,7 @@ static int enqueue_sweep(btf_engine* e) {
     const void* wt = gauss ? (const void*)e->cnt : (const void*)e->omega;
     if ((mask & BTF_SAMPLE_W) && e->nloc > 0) {
         if (e->i8_on) {
+            for (int q = 0; q < 3; ++q) e->i8.ev[q] = e->time_phases ? e->i8_ev[0][q] : nullptr;
             if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
                                 e->row_stats, st))
                 return set_err(BTF_ECUDA, "integer row statistics failed to launch");
@@ -822,6 +826,7 @@ static int enqueue_sweep(btf_engine* e) {
     if (mask & BTF_SAMPLE_V) {
         int nsplit = e->plan_col.nsplit;
         if (e->i8_on) {
+            for (int q = 0; q < 3; ++q) e->i8.ev[q] = e->time_phases ? e->i8_ev[1][q] : nullptr;
             if (launch_stats_i8(e->i8, true, e->K, e->cntT, e->nloc_pad, e->S, e->Ppad, e->W + (size_t)c.row_begin * e->K,
                                 e->nloc, e->nloc_pad, e->P, e->Ppad, e->col_stats, st))
                 return set_err(BTF_ECUDA, "integer column statistics failed to launch");
@@ -991,9 +996,21 @@ int btf_time_phases(btf_engine* e, int32_t nsweeps, double* ms_out, int32_t npha
             if (cudaEventElapsedTime(&ms, e->ph_ev[i], e->ph_ev[i + 1]) == cudaSuccess) ms_out[i] += ms;
             else cudaGetLastError();
         }
+        // sub-phases of the integer statistics path: int8 GEMM and FP64 linear block, rows then columns
+        if (e->i8_on && nphases >= PH_COUNT + 4) {
+            const int msk = e->cfg.sample_mask;
+            for (int rc2 = 0; rc2 < 2; ++rc2) {
+                if (!(msk & (rc2 == 0 ? BTF_SAMPLE_W : BTF_SAMPLE_V))) continue;
+                for (int q = 0; q < 2; ++q) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, e->i8_ev[rc2][q], e->i8_ev[rc2][q + 1]) == cudaSuccess) ms_out[PH_COUNT + 2 * rc2 + q] += ms;
+                    else cudaGetLastError();
+                }
+            }
+        }
     }
     e->time_phases = false;
-    for (int i = 0; i < PH_COUNT; ++i) ms_out[i] /= std::max(1, nsweeps);
+    for (int i = 0; i < nphases; ++i) ms_out[i] /= std::max(1, nsweeps);
     if (rc) return rc;
     return check_info(e);
 }

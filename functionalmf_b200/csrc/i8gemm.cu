@@ -224,25 +224,26 @@ extern "C" double btf_i8gemm_test(int device, const int8_t* A, const int8_t* B, 
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     int8_t *dA = nullptr, *dB = nullptr;
     int32_t* dD = nullptr;
-    const size_t na = (size_t)M * K, nb = (size_t)N * K, nd = (size_t)M * N;
+    const long long ldd = (N + 3) & ~3;                      // rows of D start on 16-byte boundaries
+    const size_t na = (size_t)M * K, nb = (size_t)N * K, nd = (size_t)M * ldd;
     if (cudaMalloc(&dA, na) || cudaMalloc(&dB, nb) || cudaMalloc(&dD, nd * 4)) return -2.0;
     cudaMemcpy(dA, A, na, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, B, nb, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0xff, nd * 4);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = launch_i8gemm(dA, K, M, dB, K, N, K, dD, N, 0);
+    int rc = launch_i8gemm(dA, K, M, dB, K, N, K, dD, ldd, 0);
     if (rc || cudaDeviceSynchronize() != cudaSuccess) {
         fprintf(stderr, "i8gemm: rc %d, %s\n", rc, cudaGetErrorString(cudaGetLastError()));
         return -3.0;
     }
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) launch_i8gemm(dA, K, M, dB, K, N, K, dD, N, 0);
+    for (int r = 0; r < reps; ++r) launch_i8gemm(dA, K, M, dB, K, N, K, dD, ldd, 0);
     cudaEventRecord(e1);
     if (cudaDeviceSynchronize() != cudaSuccess) return -4.0;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaMemcpy(D, dD, nd * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy2D(D, (size_t)N * 4, dD, (size_t)ldd * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost);
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return (double)ms;

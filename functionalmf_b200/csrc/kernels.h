@@ -51,6 +51,7 @@ struct StatsI8Buffers {
     int32_t* D;                     // [8 L][m_pad] exact digit-plane contractions
     double* bpart;                  // [nsplit][m][K] partial sums of the linear block
     int nsplit_b_row;
+    cudaEvent_t ev[3];              // optional timers: before the GEMM, after the GEMM, after the linear block (null: off)
 };
 bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col);
 void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes* s);

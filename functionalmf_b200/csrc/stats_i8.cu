@@ -237,8 +237,7 @@ void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_v
 }  // namespace
 
 bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col) {
-    static const bool off = getenv("BTF_STATS_NO_I8") != nullptr;
-    if (off) return false;
+    if (getenv("BTF_STATS_NO_I8") != nullptr) return false;      // read per data set, so a process can switch
     if (!(K == 8 || K == 16 || K == 32)) return false;
     if (nreps < 1 || nreps > 127) return false;
     const long long kd = kdim_row > kdim_col ? kdim_row : kdim_col;
@@ -277,7 +276,9 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
         zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, ldk);
     }
     // 2. exact product block on the tensor cores
+    if (w.ev[0]) cudaEventRecord(w.ev[0], st);
     if (launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st)) return 1;
+    if (w.ev[1]) cudaEventRecord(w.ev[1], st);
     // 3. linear block in FP64
     const int nchunks = kdim_pad / 64;
     const int nsplit = trans ? 1 : w.nsplit_b_row;
@@ -285,6 +286,7 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
     if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
+    if (w.ev[2]) cudaEventRecord(w.ev[2], st);
     // 4. recombination
     i8_combine_kernel<<<dim3((m_valid + 31) / 32, (L + 31) / 32 + 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;

@@ -1,0 +1,145 @@
+"""Integer-tensor-core statistics path (i8gemm.cu, stats_i8.cu).
+
+* the tcgen05 int8 GEMM is bit-exact against numpy integer arithmetic (ragged shapes included);
+* the product block of the sufficient statistics equals, BIT FOR BIT, the correctly rounded value
+  of the fixed-point sum it is defined as (checked in Python big-integer arithmetic);
+* a sweep on the integer path equals the same sweep on the FP64 DMMA path to rounding.
+"""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(A, B):
+    from functionalmf_b200 import _lib as L
+    lib = L.load()
+    M, K = A.shape
+    N = B.shape[0]
+    D = np.zeros((M, N), dtype=np.int32)
+    ms = lib.btf_i8gemm_test(0, C.c_void_p(A.ctypes.data), C.c_void_p(B.ctypes.data), C.c_void_p(D.ctypes.data), M, N, K, 1)
+    assert ms >= 0
+    return D
+
+
+@pytest.mark.parametrize('shape', [(128, 256, 128), (1, 1, 128), (130, 257, 384), (200, 300, 1024), (1088, 520, 2048)])
+def test_i8gemm_exact(shape):
+    M, N, K = shape
+    rs = np.random.RandomState(M + N + K)
+    A = rs.randint(-64, 64, size=(M, K)).astype(np.int8)
+    B = rs.randint(0, 4, size=(N, K)).astype(np.int8)
+    np.testing.assert_array_equal(_gemm(A, B), A.astype(np.int32) @ B.astype(np.int32).T)
+    # extreme digits and counts: the int32 accumulators hold them exactly
+    A[:] = -64
+    B[:] = 127
+    np.testing.assert_array_equal(_gemm(A, B), np.full((M, N), -64 * 127 * K, dtype=np.int32))
+
+
+def _engine(N, M, T, R, K, env):
+    from functionalmf_b200.engine import Engine
+    for k in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8'):
+        os.environ.pop(k, None)
+    os.environ[env] = '1'
+    return Engine(N, M, T, nembeds=K, tf_order=2, seed=5, use_graph=0)
+
+
+def _problem(N, M, T, R, K, seed):
+    rs = np.random.RandomState(seed)
+    W = rs.normal(size=(N, K))
+    V = rs.normal(size=(M, T, K)).cumsum(axis=1) * 0.3
+    Y = np.einsum('nk,mtk->nmt', W, V)[..., None] + rs.normal(size=(N, M, T, R))
+    Y[rs.random_sample(Y.shape) < 0.25] = np.nan
+    RD = None
+    return rs, W, V, Y
+
+
+def _load(eng, rs, W, V):
+    RD = eng.RD
+    M = V.shape[0]
+    eng.set('W', W * 0.9)
+    eng.set('V', V * 1.1)
+    for k in ('Tau2', 'Tau2_a', 'Tau2_b', 'Tau2_c'):
+        eng.set(k, np.random.RandomState(3).gamma(2.0, size=(M, RD)) + 0.05)
+    for k, v in dict(lam2=0.7, lam2_a=1.3, sigma2=0.9, nu2=1.1).items():
+        eng.set(k, [v])
+
+
+@pytest.mark.parametrize('shape', [(150, 9, 21, 3, 8), (300, 7, 40, 2, 16), (129, 5, 33, 4, 32)])
+def test_product_block_is_the_exact_fixed_point_sum(shape):
+    N, M, T, R, K = shape
+    rs, W, V, Y = _problem(N, M, T, R, K, 11)
+    eng = _engine(N, M, T, R, K, 'BTF_STATS_FORCE_I8')
+    try:
+        eng.set_data_gaussian(Y)
+        _load(eng, rs, W, V)
+        eng.enable_diag(True)
+        from functionalmf_b200 import _lib as L
+        eng.set_sample_mask(L.SAMPLE_W | L.SAMPLE_V)      # W and V steps only
+        z = np.zeros(N * K)
+        eng.inject('z_W', z)                  # W stays at its conditional mean: the V statistics use a known W
+        eng.sweep(1)
+        L = K * (K + 1) // 2
+        cnt = (~np.isnan(Y)).sum(axis=-1).reshape(N, M * T)
+        Ssum = np.nansum(Y, axis=-1).reshape(N, M * T)
+
+        def exact(F, counts):
+            """counts [m, k], F [k, K] -> [m, L] correctly rounded fixed-point sums, Python integers"""
+            out = np.zeros((counts.shape[0], L))
+            c = 0
+            for k1 in range(K):
+                for k2 in range(k1 + 1):
+                    z = F[:, k1] * F[:, k2]
+                    mx = np.abs(z).max()
+                    e = int(np.floor(np.log2(mx))) + 1 if mx > 0 else 0
+                    while mx >= 2.0 ** e:
+                        e += 1
+                    while e > -1070 and mx < 2.0 ** (e - 1):
+                        e -= 1
+                    q = [int(np.rint(np.ldexp(v, 54 - e))) for v in z]
+                    for m in range(counts.shape[0]):
+                        tot = sum(int(cc) * qq for cc, qq in zip(counts[m], q) if cc)
+                        out[m, c] = float(np.ldexp(np.float64(tot), e - 54)) if abs(tot) < 2 ** 53 else float(tot) * 2.0 ** (e - 54)
+                    c += 1
+            return out
+
+        rows = eng.diag('row_stats')
+        Vf = (V * 1.1).reshape(M * T, K)
+        want = exact(Vf, cnt)
+        np.testing.assert_array_equal(rows[:, :L], want)
+        # linear block: plain FP64
+        np.testing.assert_allclose(rows[:, L:], Ssum @ Vf, rtol=1e-12, atol=1e-12 * np.abs(Ssum @ Vf).max())
+        cols = eng.diag('col_stats')
+        Wn = eng.get('W')
+        want = exact(Wn, cnt.T)
+        np.testing.assert_array_equal(cols[:, :L], want)
+        np.testing.assert_allclose(cols[:, L:], Ssum.T @ Wn, rtol=1e-12, atol=1e-12 * np.abs(Ssum.T @ Wn).max())
+    finally:
+        eng.close()
+        os.environ.pop('BTF_STATS_FORCE_I8', None)
+
+
+@pytest.mark.parametrize('shape', [(260, 12, 24, 3, 16), (140, 6, 30, 2, 8), (200, 5, 20, 3, 32)])
+def test_sweep_matches_the_fp64_path(shape):
+    N, M, T, R, K = shape
+    rs, W, V, Y = _problem(N, M, T, R, K, 21)
+    res = {}
+    for env in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8'):
+        eng = _engine(N, M, T, R, K, env)
+        try:
+            eng.set_data_gaussian(Y)
+            _load(eng, rs, W, V)
+            eng.enable_diag(True)
+            eng.sweep(2)
+            res[env] = dict(W=eng.get('W'), V=eng.get('V'), Tau2=eng.get('Tau2'), nu2=eng.get_scalar('nu2'),
+                            sigma2=eng.get_scalar('sigma2'), rows=eng.diag('row_stats'), cols=eng.diag('col_stats'))
+        finally:
+            eng.close()
+            os.environ.pop(env, None)
+    a, b = res['BTF_STATS_FORCE_I8'], res['BTF_STATS_NO_I8']
+    for k in ('rows', 'cols'):
+        np.testing.assert_allclose(a[k], b[k], rtol=0, atol=1e-11 * np.abs(b[k]).max())
+    for k in ('W', 'V', 'Tau2'):
+        assert np.max(np.abs(a[k] - b[k])) <= 1e-8 * np.max(np.abs(b[k])), k
+    assert a['nu2'] == pytest.approx(b['nu2'], rel=1e-9) and a['sigma2'] == pytest.approx(b['sigma2'], rel=1e-9)
