@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of i8gemm_kernel (mean of the row and the column launch)
 # from the ncu --set full capture of the same command (profiles/); None until captured
-I8_TRAFFIC = {}
+I8_TRAFFIC = {('c2', 1): 4.325e8}     # profiles/r1_ncu_i8_summary.txt: rows 0.340 + 0.005 GB, columns 0.273 + 0.247 GB
 
 WORKLOADS = {
     # name: N, M, T, R, K, order, nan_frac

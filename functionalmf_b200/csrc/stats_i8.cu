@@ -98,23 +98,27 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
     }
 }
 
-// out[split][m][j] = sum_k S[m,k] F[k,j] over the split's k range: FP64 tensor pipe, HBM bound
+// out[split][m][j] = sum_k S[m,k] F[k,j] over the split's k range: FP64 tensor pipe, HBM bound.
+// 128 rows x 32 contraction elements per stage; a warp owns 16 rows x all columns = 2 CT independent
+// accumulator chains (the FP64 mma has a long latency: two chains left the pipe 40 % idle).
 template <int KB, bool TRANS>
 __global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ F,
                                                     int K, int m_valid, int nchunks, int chunks_per_split,
                                                     double* __restrict__ out) {
-    constexpr int BM = 64, KC = 64, SS = 68, FS = KB + 4, CT = KB / 8;
+    constexpr int BM = 128, KC = 32, FS = KB + 4, CT = KB / 8;
+    constexpr int SROWS = TRANS ? KC : BM, SCOLS = TRANS ? BM : KC, SS = SCOLS + 4;   // strides = 4 (mod 16) doubles
     extern __shared__ __align__(16) double smf[];
-    double* Ssm = smf;                       // [2][64][SS]   (!TRANS: [m][k], TRANS: [k][m])
-    double* Fsm = smf + 2 * 64 * SS;         // [2][KC][FS]
+    double* Ssm = smf;                       // [2][SROWS][SS]   (!TRANS: [m][k], TRANS: [k][m])
+    double* Fsm = smf + 2 * SROWS * SS;      // [2][KC][FS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * BM;
     const int c_begin = blockIdx.y * chunks_per_split, c_end = min(nchunks, c_begin + chunks_per_split);
     auto load = [&](int stage, int chunk) {
         const long long k0 = (long long)chunk * KC;
-        double* sd = Ssm + stage * 64 * SS;
-        for (int e = tid; e < 64 * 32; e += 256) {
-            const int r = e >> 5, q = e & 31;
+        double* sd = Ssm + stage * SROWS * SS;
+        constexpr int CPR = SCOLS / 2;       // 16-byte copies per row
+        for (int e = tid; e < SROWS * CPR; e += 256) {
+            const int r = e / CPR, q = e - r * CPR;
             const double* src = TRANS ? S + (k0 + r) * lds + m0 + 2 * q : S + (long long)(m0 + r) * lds + k0 + 2 * q;
             cp_async16(sd + r * SS + 2 * q, src);
         }
@@ -124,9 +128,11 @@ __global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S
             cp_async16(fd + r * FS + cidx, F + (k0 + r) * K + cidx);
         }
     };
-    double acc[CT][2];
+    double acc[2][CT][2];
 #pragma unroll
-    for (int c = 0; c < CT; ++c) acc[c][0] = acc[c][1] = 0.0;
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
     // zero the padding columns of the F tiles once (K < KB)
     for (int e = tid; e < 2 * KC * FS; e += 256) Fsm[e] = 0.0;
     __syncthreads();
@@ -138,29 +144,37 @@ __global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const double* sd = Ssm + stg * 64 * SS;
+        const double* sd = Ssm + stg * SROWS * SS;
         const double* fd = Fsm + stg * KC * FS;
-        const int ml = warp * 8 + (lane >> 2);
-#pragma unroll 4
+        const int ml = warp * 16 + (lane >> 2);
+#pragma unroll
         for (int kk = 0; kk < KC / 4; ++kk) {
             const int kl = kk * 4 + (lane & 3);
-            const double av = TRANS ? sd[kl * SS + ml] : sd[ml * SS + kl];
+            const double a0 = TRANS ? sd[kl * SS + ml] : sd[ml * SS + kl];
+            const double a1 = TRANS ? sd[kl * SS + ml + 8] : sd[(ml + 8) * SS + kl];
 #pragma unroll
-            for (int ct = 0; ct < CT; ++ct) dmma(acc[ct][0], acc[ct][1], av, fd[kl * FS + ct * 8 + (lane >> 2)]);
+            for (int ct = 0; ct < CT; ++ct) {
+                const double bv = fd[kl * FS + ct * 8 + (lane >> 2)];
+                dmma(acc[0][ct][0], acc[0][ct][1], a0, bv);
+                dmma(acc[1][ct][0], acc[1][ct][1], a1, bv);
+            }
         }
         __syncthreads();
     }
     cp_async_wait<0>();
-    const int m = m0 + warp * 8 + (lane >> 2);
-    if (m < m_valid) {
-        double* o = out + ((long long)blockIdx.y * m_valid + m) * K;
 #pragma unroll
-        for (int ct = 0; ct < CT; ++ct)
+    for (int r = 0; r < 2; ++r) {
+        const int m = m0 + warp * 16 + r * 8 + (lane >> 2);
+        if (m < m_valid) {
+            double* o = out + ((long long)blockIdx.y * m_valid + m) * K;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = ct * 8 + (lane & 3) * 2 + h;
-                if (j < K) o[j] = acc[ct][h];
-            }
+            for (int ct = 0; ct < CT; ++ct)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = ct * 8 + (lane & 3) * 2 + h;
+                    if (j < K) o[j] = acc[r][ct][h];
+                }
+        }
     }
 }
 
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t* __rest
 template <int KB, bool TRANS>
 void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks,
                  int nsplit, double* out, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * 64 * 68 + 2 * 64 * (KB + 4)) * sizeof(double);
+    const size_t smem = (size_t)(2 * (TRANS ? 32 * 132 : 128 * 36) + 2 * 32 * (KB + 4)) * sizeof(double);
     auto kern = sf_kernel<KB, TRANS>;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
@@ -250,7 +264,7 @@ void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes
     s->planes_bytes = (size_t)(NPLANES * L * kd);
     s->d_elems = (size_t)(NPLANES * L * nd);
     s->cntT_bytes = (size_t)P * nloc_pad;
-    s->nsplit_b_row = 4;
+    s->nsplit_b_row = 8;
     s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)P * K);
     s->L = (int)L;
 }
@@ -280,9 +294,9 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
     if (launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st)) return 1;
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
     // 3. linear block in FP64
-    const int nchunks = kdim_pad / 64;
+    const int nchunks = kdim_pad / 32;
     const int nsplit = trans ? 1 : w.nsplit_b_row;
-    const int m_tiles = (m_valid + 63) / 64;
+    const int m_tiles = (m_valid + 127) / 128;
     if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
