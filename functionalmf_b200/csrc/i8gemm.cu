@@ -75,6 +75,7 @@ struct I8Args {
     const int8_t* B; long long ldb; int N;       // counts   [N][ldb]
     int K;                                       // multiple of 128 (both operands readable up to K)
     int32_t* D; long long ldd;                   // [M][ldd]
+    int chunks_per_split;                        // gridDim.z > 1: split-K, partial tiles are added with integer atomics (exact, order independent)
 };
 
 }  // namespace
@@ -89,7 +90,9 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * I8_BM, n0 = blockIdx.y * I8_BN;
-    const int nchunks = p.K / I8_BK;
+    const int c_first = blockIdx.z * p.chunks_per_split;
+    const int nchunks = min(p.K / I8_BK - c_first, p.chunks_per_split);     // this CTA's share of the contraction
+    const bool split = gridDim.z > 1;
 
     if (tid == 0) {
         for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 128); mbar_init(empty + s, 1); }
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
             const int s = c % I8_STAGES;
             uint8_t* sa = sm + s * I8_STAGE_BYTES;
             uint8_t* sb = sa + I8_A_BYTES;
-            const long long k0 = (long long)c * I8_BK;
+            const long long k0 = (long long)(c_first + c) * I8_BK;
 #pragma unroll
             for (int j = 0; j < (I8_BM + I8_BN) * 8 / 128; ++j) {
                 const int q = pt + 128 * j;
@@ -182,7 +185,11 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
             if (row < p.M) {
                 int32_t* drow = p.D + (long long)row * p.ldd + n0 + j * 32;
-                if (n0 + j * 32 + 32 <= p.N) {
+                if (split) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (n0 + j * 32 + q < p.N && v[q] != 0u) atomicAdd(drow + q, (int)v[q]);
+                } else if (n0 + j * 32 + 32 <= p.N) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<int4*>(drow + 4 * q) = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
@@ -210,8 +217,22 @@ int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long l
         if (cudaFuncSetAttribute(i8gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return 2;
         attr_set = true;
     }
-    I8Args p{A, lda, M, B, ldb, N, K, D, ldd};
-    dim3 grid((M + I8_BM - 1) / I8_BM, (N + I8_BN - 1) / I8_BN);
+    const int mt = (M + I8_BM - 1) / I8_BM, nt = (N + I8_BN - 1) / I8_BN, nchunks = K / I8_BK;
+    // split-K when the tiles alone cannot fill the GPU (few rows: multi-GPU shards, small tensors)
+    int nsplit = 1;
+    if (mt * nt < 148) {
+        nsplit = 148 / (mt * nt);
+        const int cap = nchunks / 8 > 0 ? nchunks / 8 : 1;      // keep at least 8 chunks per CTA
+        if (nsplit > cap) nsplit = cap;
+        if (nsplit < 1) nsplit = 1;
+    }
+    const int cps = (nchunks + nsplit - 1) / nsplit;
+    nsplit = (nchunks + cps - 1) / cps;
+    if (nsplit > 1) {
+        if (cudaMemsetAsync(D, 0, (size_t)M * ldd * sizeof(int32_t), st) != cudaSuccess) return 4;
+    }
+    I8Args p{A, lda, M, B, ldb, N, K, D, ldd, cps};
+    dim3 grid(mt, nt, nsplit);
     i8gemm_kernel<<<grid, 160, I8_SMEM, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

@@ -36,18 +36,28 @@ __device__ __forceinline__ void pair_of(int c, int& k1, int& k2) {
     k2 = c - k1 * (k1 + 1) / 2;
 }
 
-// colmax[c] = max_r |F[r,k1] F[r,k2]| (bit pattern of a non-negative double, so an integer max is exact)
+// colmax[c] = max_r |F[r,k1] F[r,k2]| (bit pattern of a non-negative double, so an integer max is exact).
+// A block stages 128 rows of F in shared memory; thread c (and c + 256, ...) scans them.
 __global__ void __launch_bounds__(256) zmax_kernel(const double* __restrict__ F, int rows, int K, int L,
                                                    unsigned long long* __restrict__ colmax) {
-    const int c = blockIdx.y * 256 + threadIdx.x;
-    int k1 = 0, k2 = 0;
-    if (c < L) pair_of(c, k1, k2);
-    double m = 0.0;
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        const double* fr = F + (long long)r * K;
-        if (c < L) m = fmax(m, fabs(fr[k1] * fr[k2]));
+    extern __shared__ __align__(16) double zms[];
+    const int rb = blockIdx.x * 128;
+    const int nr = min(128, rows - rb);
+    for (int e = threadIdx.x; e < nr * K; e += 256) zms[e] = F[(long long)rb * K + e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < L; c += 256) {
+        int k1, k2;
+        pair_of(c, k1, k2);
+        double m0 = 0.0, m1 = 0.0;
+        int r = 0;
+        for (; r + 2 <= nr; r += 2) {
+            m0 = fmax(m0, fabs(zms[r * K + k1] * zms[r * K + k2]));
+            m1 = fmax(m1, fabs(zms[(r + 1) * K + k1] * zms[(r + 1) * K + k2]));
+        }
+        if (r < nr) m0 = fmax(m0, fabs(zms[r * K + k1] * zms[r * K + k2]));
+        const double m = fmax(m0, m1);
+        if (m > 0.0) atomicMax(colmax + c, (unsigned long long)__double_as_longlong(m));
     }
-    if (c < L && m > 0.0) atomicMax(colmax + c, (unsigned long long)__double_as_longlong(m));
 }
 
 // digit planes: planes[(s L + c) ldk + r] = d_s of q[r, c].  A block stages 256 rows of F in shared memory;
@@ -264,7 +274,7 @@ void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes
     s->planes_bytes = (size_t)(NPLANES * L * kd);
     s->d_elems = (size_t)(NPLANES * L * nd);
     s->cntT_bytes = (size_t)P * nloc_pad;
-    s->nsplit_b_row = 8;
+    s->nsplit_b_row = 64;            // upper bound of the split count of the row-variant linear block (buffer size)
     s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)P * K);
     s->L = (int)L;
 }
@@ -282,7 +292,7 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
     const long long ldk = kdim_pad, ldn = m_pad;
     // 1. column scales and digit planes of Z
     cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
-    zmax_kernel<<<dim3(148 * 4, (L + 255) / 256), 256, 0, st>>>(F, f_rows, K, L, w.colmax);
+    zmax_kernel<<<(f_rows + 127) / 128, 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
     {
         const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
         static size_t zs_set = 0;
@@ -295,8 +305,15 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
     // 3. linear block in FP64
     const int nchunks = kdim_pad / 32;
-    const int nsplit = trans ? 1 : w.nsplit_b_row;
     const int m_tiles = (m_valid + 127) / 128;
+    // enough CTAs for two per SM; split-K partials are summed in split order by the recombination kernel
+    int nsplit = 1;
+    if (m_tiles < 296) {
+        nsplit = 296 / m_tiles;          // one full wave of two CTAs per SM, never a partial second wave
+        if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
+        if (nsplit > (trans ? 1 : w.nsplit_b_row)) nsplit = trans ? 1 : w.nsplit_b_row;
+    }
+    { const int cps = (nchunks + nsplit - 1) / nsplit; nsplit = (nchunks + cps - 1) / cps; }
     if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }

@@ -24,7 +24,7 @@ def _gemm(A, B):
     return D
 
 
-@pytest.mark.parametrize('shape', [(128, 256, 128), (1, 1, 128), (130, 257, 384), (200, 300, 1024), (1088, 520, 2048)])
+@pytest.mark.parametrize('shape', [(128, 256, 128), (1, 1, 128), (130, 257, 384), (200, 300, 1024), (1088, 520, 2048), (128, 256, 8192), (300, 100, 16384)])
 def test_i8gemm_exact(shape):
     M, N, K = shape
     rs = np.random.RandomState(M + N + K)
