@@ -94,11 +94,13 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const double* fr = Fs + (4 * tx + u) * KS;
-            long long q = __double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e));
+            // signed base-128 digits without a carry chain: add 64 at every digit position (C = sum_s 64 128^s
+            // < 2^55.1, so q + C is in (0, 2^56)), read the unsigned 7-bit fields, subtract 64 from each
+            const unsigned long long qq =
+                (unsigned long long)(__double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e)) + 0x0081020408102040ll);
 #pragma unroll
             for (int s = 0; s < NPLANES; ++s) {
-                const long long d = ((q + 64) & 127) - 64;          // signed digit in [-64, 63]
-                q = (q - d) >> 7;
+                const int d = (int)((qq >> (7 * s)) & 127ull) - 64;   // in [-64, 63]
                 dig[s] |= ((unsigned)(d & 0xff)) << (8 * u);
             }
         }
