@@ -693,6 +693,9 @@ static int ensure_i8(btf_engine* e) {
     if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
                         e->row_stats, e->stream))
         return set_err(BTF_ECUDA, "integer statistics path failed to launch");
+    if (launch_stats_i8(e->i8, true, e->K, e->cntT, e->nloc_pad, e->S, e->Ppad, e->W + (size_t)e->cfg.row_begin * e->K,
+                        e->nloc, e->nloc_pad, e->P, e->Ppad, e->col_stats, e->stream))
+        return set_err(BTF_ECUDA, "integer statistics path failed to launch");
     CK(cudaStreamSynchronize(e->stream));
     e->i8_on = true;
     free_graph(e);
