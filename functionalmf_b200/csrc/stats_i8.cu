@@ -23,6 +23,8 @@ namespace btf {
 
 int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
                   long long ldd, cudaStream_t st);
+int launch_i8gemm_fused(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K,
+                        const int* expo, double* out, long long ldo, int min_tiles, cudaStream_t st);
 
 namespace {
 
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) zmax_kernel(const double* __restrict__ F,
     }
 }
 
-// digit planes: planes[(s L + c) ldk + r] = d_s of q[r, c].  A block stages 256 rows of F in shared memory;
+// digit planes, interleaved: planes[(8 c + s) ldk + r] = d_s of q[r, c].  A block stages 256 rows of F in shared memory;
 // thread (tx, ty): rows 4 tx .. 4 tx + 3 (one 4-byte store per plane), columns c = ty, ty + 4, ...
 __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ F, int rows, int rows_pad, int K, int L,
                                                       const unsigned long long* __restrict__ colmax,
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
         }
 #pragma unroll
         for (int s = 0; s < NPLANES; ++s)
-            *reinterpret_cast<unsigned*>(planes + ((long long)s * L + c) * ldk + r0) = dig[s];
+            *reinterpret_cast<unsigned*>(planes + ((long long)c * NPLANES + s) * ldk + r0) = dig[s];
     }
 }
 
@@ -190,22 +192,22 @@ __global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S
     }
 }
 
-// out[m][c] = 2^(e_c - 54) sum_s 128^s D[(s L + c) ldn + m]  (32 x 32 tiles through shared memory),
+// out[m][c] = 2^(e_c - 54) sum_s 128^s D[(8 c + s) ldn + m]  (32 x 32 tiles through shared memory),
 // out[m][L + j] = sum_split bpart[split][m][j]
 __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restrict__ D, long long ldn, const int* __restrict__ expo,
                                                          const double* __restrict__ bpart, int nsplit_b, int m_valid, int L,
-                                                         int K, double* __restrict__ out) {
+                                                         int K, double* __restrict__ out, int first_cy) {
     __shared__ double tile[32][33];
     const int nco = L + K;
-    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int m0 = blockIdx.x * 32, c0 = (blockIdx.y + first_cy) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
     if (c0 < L) {
         for (int cy = ty; cy < 32; cy += 8) {
             const int c = c0 + cy, m = m0 + tx;
             double v = 0.0;
             if (c < L && m < m_valid) {
-                const int32_t* d = D + (long long)c * ldn + m;
-                const long long pl = (long long)L * ldn;
+                const int32_t* d = D + (long long)c * NPLANES * ldn + m;
+                const long long pl = ldn;
                 long long hi = d[7 * pl], lo = d[3 * pl];
                 hi = hi * 128 + d[6 * pl]; lo = lo * 128 + d[2 * pl];
                 hi = hi * 128 + d[5 * pl]; lo = lo * 128 + d[1 * pl];
@@ -301,9 +303,18 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
         if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
         zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, ldk);
     }
-    // 2. exact product block on the tensor cores
+    // 2. exact product block on the tensor cores: fused (counts on the M side, recombination in the epilogue) when
+    //    its tiles fill the GPU, else through the int32 intermediate with split-K
     if (w.ev[0]) cudaEventRecord(w.ev[0], st);
-    if (launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st)) return 1;
+    const bool no_fused = getenv("BTF_STATS_I8_NOFUSED") != nullptr, force_fused = getenv("BTF_STATS_I8_FUSED") != nullptr;
+    // (measured on C2: the fused epilogue's FP64 stores are not hidden under the next tile, 0.29 + 0.50 ms against
+    //  0.27 + 0.35 ms + 0.08 ms of recombination, so the int32 route is the default and the fused one is opt-in)
+    int fused = (no_fused || !force_fused) ? 1 : launch_i8gemm_fused(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, ldk, L,
+                                                                     kdim_pad, w.expo, out, L + K, 0, st);
+    if (fused > 1) return 1;
+    if (fused == 1 &&
+        launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st))
+        return 1;
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
     // 3. linear block in FP64
     const int nchunks = kdim_pad / 32;
@@ -320,8 +331,12 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
     else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
     if (w.ev[2]) cudaEventRecord(w.ev[2], st);
-    // 4. recombination
-    i8_combine_kernel<<<dim3((m_valid + 31) / 32, (L + 31) / 32 + 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out);
+    // 4. recombination of the int32 planes (not on the fused path) and the sum of the linear-block partials
+    const int ncy = (L + 31) / 32;
+    if (fused == 0)
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out, ncy);
+    else
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out, 0);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

@@ -37,11 +37,16 @@ def test_i8gemm_exact(shape):
     np.testing.assert_array_equal(_gemm(A, B), np.full((M, N), -64 * 127 * K, dtype=np.int32))
 
 
-def _engine(N, M, T, R, K, env):
+GEMM_MODES = ('BTF_STATS_I8_FUSED', 'BTF_STATS_I8_NOFUSED')   # recombination in the GEMM epilogue / through the int32 planes
+
+
+def _engine(N, M, T, R, K, env, gemm_mode=None):
     from functionalmf_b200.engine import Engine
-    for k in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8'):
+    for k in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8') + GEMM_MODES:
         os.environ.pop(k, None)
     os.environ[env] = '1'
+    if gemm_mode:
+        os.environ[gemm_mode] = '1'
     return Engine(N, M, T, nembeds=K, tf_order=2, seed=5, use_graph=0)
 
 
@@ -66,11 +71,12 @@ def _load(eng, rs, W, V):
         eng.set(k, [v])
 
 
+@pytest.mark.parametrize('gemm_mode', GEMM_MODES)
 @pytest.mark.parametrize('shape', [(150, 9, 21, 3, 8), (300, 7, 40, 2, 16), (129, 5, 33, 4, 32)])
-def test_product_block_is_the_exact_fixed_point_sum(shape):
+def test_product_block_is_the_exact_fixed_point_sum(shape, gemm_mode):
     N, M, T, R, K = shape
     rs, W, V, Y = _problem(N, M, T, R, K, 11)
-    eng = _engine(N, M, T, R, K, 'BTF_STATS_FORCE_I8')
+    eng = _engine(N, M, T, R, K, 'BTF_STATS_FORCE_I8', gemm_mode)
     try:
         eng.set_data_gaussian(Y)
         _load(eng, rs, W, V)
@@ -117,16 +123,18 @@ def test_product_block_is_the_exact_fixed_point_sum(shape):
         np.testing.assert_allclose(cols[:, L:], Ssum.T @ Wn, rtol=1e-12, atol=1e-12 * np.abs(Ssum.T @ Wn).max())
     finally:
         eng.close()
-        os.environ.pop('BTF_STATS_FORCE_I8', None)
+        for k in ('BTF_STATS_FORCE_I8',) + GEMM_MODES:
+            os.environ.pop(k, None)
 
 
+@pytest.mark.parametrize('gemm_mode', GEMM_MODES)
 @pytest.mark.parametrize('shape', [(260, 12, 24, 3, 16), (140, 6, 30, 2, 8), (200, 5, 20, 3, 32)])
-def test_sweep_matches_the_fp64_path(shape):
+def test_sweep_matches_the_fp64_path(shape, gemm_mode):
     N, M, T, R, K = shape
     rs, W, V, Y = _problem(N, M, T, R, K, 21)
     res = {}
     for env in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8'):
-        eng = _engine(N, M, T, R, K, env)
+        eng = _engine(N, M, T, R, K, env, gemm_mode)
         try:
             eng.set_data_gaussian(Y)
             _load(eng, rs, W, V)
@@ -136,7 +144,8 @@ def test_sweep_matches_the_fp64_path(shape):
                             sigma2=eng.get_scalar('sigma2'), rows=eng.diag('row_stats'), cols=eng.diag('col_stats'))
         finally:
             eng.close()
-            os.environ.pop(env, None)
+            for k in (env,) + GEMM_MODES:
+                os.environ.pop(k, None)
     a, b = res['BTF_STATS_FORCE_I8'], res['BTF_STATS_NO_I8']
     for k in ('rows', 'cols'):
         np.testing.assert_allclose(a[k], b[k], rtol=0, atol=1e-11 * np.abs(b[k]).max())
