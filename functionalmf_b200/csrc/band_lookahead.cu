@@ -62,7 +62,8 @@ struct LaGeom {
     static constexpr int MINB = KB > 16 ? 1 : 4;
     static constexpr int COLE = (Q + 1) * KK;              // global block column: Linv_t | L_1t .. L_Qt
     static constexpr int BWD = COLE + KB;                  // + y_t : one backward stage
-    static constexpr int WREG = NBLK * BLK > 2 * BWD ? NBLK * BLK : 2 * BWD;
+    static constexpr int NST = 3;                          // backward stages: the block column of step t-2 is in flight during step t
+    static constexpr int WREG = NBLK * BLK > NST * BWD ? NBLK * BLK : NST * BWD;
     static constexpr int NSW = TB <= 2 ? TB : 1;           // 8-row strips a worker warp runs together (independent tensor-pipe chains)
     static constexpr int PF = (KB * (KB + 1) / 2 + NWT - 1) / NWT;   // prefetched statistics per worker thread
     __host__ __device__ static constexpr int base(int d) { return d * (Q + 1) - d * (d - 1) / 2; }
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     const int jl = blockIdx.x, jg = a.col_begin + jl;
     const unsigned full = 0xffffffffu;
 
-    double* Wb = sm;                                   // [NBLK][BLK] window  (backward: 2 stages of BWD)
+    double* Wb = sm;                                   // [NBLK][BLK] window  (backward: NST stages of BWD)
     double* Li = Wb + G::WREG;                         // [2][BLK]   inverse of the diagonal factor (padded rows)
     double* bw = Li + 2 * BLK;                         // [Q+1][KB]  right-hand-side window
     double* ycur = bw + (Q + 1) * KB;                  // [KB]
@@ -564,7 +565,8 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     // ---- backward substitution by block columns: x_t = Linv_t^T (w_t - sum_u L_ut^T x_{t+u})
     // warp 0: the draw (w = y + z); warp 1: the conditional mean (w = y), only when asked for;
     // warp 2: the normals of the next step
-    double* Lc = Wb;                                   // [2][BWD]
+    double* Lc = Wb;                                   // [NST][BWD]
+    constexpr int NST = G::NST;
     const unsigned long long sweep = a.scal->sweep;
     double* Vout = a.V + (size_t)jg * n;
     const bool want_mean = a.diag_mean != nullptr;
@@ -584,15 +586,18 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
             zb[(t & 1) * KB + lane] = z;
         }
     };
-    fetch(T - 1, (T - 1) & 1);
+    // prefetch distance NST - 1 = 2 steps: one step is shorter than the latency of the factor coming back from HBM
+    fetch(T - 1, (T - 1) % NST);
+    la_cp_commit();
+    if (T > 1) fetch(T - 2, (T - 2) % NST);
     la_cp_commit();
     if (warp == 2) zgen(T - 1);
     for (int t = T - 1; t >= 0; --t) {
-        if (t > 0) fetch(t - 1, (t - 1) & 1);
+        if (t > 1) fetch(t - 2, (t - 2) % NST);
         la_cp_commit();
-        la_cp_wait<1>();
+        la_cp_wait<2>();
         __syncthreads();
-        const double* Lt = Lc + (t & 1) * BWD;
+        const double* Lt = Lc + (t % NST) * BWD;
         if (warp < 2 && (warp == 0 || want_mean)) {
             const int rhs = warp, k = lane < KB ? lane : 0;
             double r = Lt[COLE + k] + (rhs == 0 ? zb[(t & 1) * KB + k] : 0.0);
