@@ -90,25 +90,7 @@ def test_product_block_is_the_exact_fixed_point_sum(shape, gemm_mode):
         cnt = (~np.isnan(Y)).sum(axis=-1).reshape(N, M * T)
         Ssum = np.nansum(Y, axis=-1).reshape(N, M * T)
 
-        def exact(F, counts):
-            """counts [m, k], F [k, K] -> [m, L] correctly rounded fixed-point sums, Python integers"""
-            out = np.zeros((counts.shape[0], L))
-            c = 0
-            for k1 in range(K):
-                for k2 in range(k1 + 1):
-                    z = F[:, k1] * F[:, k2]
-                    mx = np.abs(z).max()
-                    e = int(np.floor(np.log2(mx))) + 1 if mx > 0 else 0
-                    while mx >= 2.0 ** e:
-                        e += 1
-                    while e > -1070 and mx < 2.0 ** (e - 1):
-                        e -= 1
-                    q = [int(np.rint(np.ldexp(v, 54 - e))) for v in z]
-                    for m in range(counts.shape[0]):
-                        tot = sum(int(cc) * qq for cc, qq in zip(counts[m], q) if cc)
-                        out[m, c] = float(np.ldexp(np.float64(tot), e - 54)) if abs(tot) < 2 ** 53 else float(tot) * 2.0 ** (e - 54)
-                    c += 1
-            return out
+        from oracle.fixed_point import product_block as exact     # the definition, in Python integers
 
         rows = eng.diag('row_stats')
         Vf = (V * 1.1).reshape(M * T, K)
