@@ -15,6 +15,7 @@
 //   warp 0, one lane:        tcgen05.mma issuer; tcgen05.commit releases a stage / publishes the accumulator
 // mbarriers: full[stage] (producers -> MMA), empty[stage] (MMA -> producers), accum (MMA -> epilogue).
 #include <cstdio>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace btf {
@@ -24,6 +25,7 @@ namespace {
 constexpr int I8_BM = 128, I8_BN = 256, I8_BK = 128, I8_STAGES = 4, I8_LAG = 2;
 constexpr int I8_A_BYTES = I8_BM * I8_BK, I8_B_BYTES = I8_BN * I8_BK, I8_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int I8_SMEM2 = 2 * I8_STAGE_BYTES + 1024 + 256;     // two-stage variant: two CTAs per SM
 constexpr int I8_TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,12 +82,16 @@ struct I8Args {
 
 }  // namespace
 
-__global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
+// STAGES = 4: one CTA per SM, deep pipeline (long contractions).  STAGES = 2: two CTAs per SM, so that one CTA's
+// prologue (tensor-memory allocation, pipeline fill) and epilogue overlap the other's main loop (short contractions).
+template <int STAGES>
+__global__ void __launch_bounds__(160, STAGES > 2 ? 1 : 2) i8gemm_kernel(I8Args p) {
+    constexpr int LAG = STAGES > 2 ? 2 : 1;
     extern __shared__ uint8_t smraw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sm + I8_STAGES * I8_STAGE_BYTES);
-    uint64_t* empty = full + I8_STAGES;
-    uint64_t* accum = empty + I8_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + STAGES * I8_STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accum = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
     const bool split = gridDim.z > 1;
 
     if (tid == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 128); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 128); mbar_init(empty + s, 1); }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -112,8 +118,8 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
         if (lane == 0) {
             // ===== MMA issuer
             for (int c = 0; c < nchunks; ++c) {
-                const int s = c % I8_STAGES;
-                mbar_wait(full + s, (uint32_t)((c / I8_STAGES) & 1));
+                const int s = c % STAGES;
+                mbar_wait(full + s, (uint32_t)((c / STAGES) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t a0 = smem_u32(sm + s * I8_STAGE_BYTES), b0 = a0 + I8_A_BYTES;
 #pragma unroll
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
         // ===== producers: 3072 16-byte copies per stage, 24 per thread; 8 consecutive threads cover one 128-byte row
         const int pt = tid - 32;
         auto issue = [&](int c) {
-            const int s = c % I8_STAGES;
+            const int s = c % STAGES;
             uint8_t* sa = sm + s * I8_STAGE_BYTES;
             uint8_t* sb = sa + I8_A_BYTES;
             const long long k0 = (long long)(c_first + c) * I8_BK;
@@ -149,18 +155,18 @@ __global__ void __launch_bounds__(160, 1) i8gemm_kernel(I8Args p) {
         auto publish = [&](int c) {
             // the copies of chunk c have landed (generic proxy) -> make them visible to the tensor core (async proxy)
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_arrive(full + (c % I8_STAGES));
+            mbar_arrive(full + (c % STAGES));
         };
         for (int c = 0; c < nchunks; ++c) {
-            if (c >= I8_STAGES) mbar_wait(empty + (c % I8_STAGES), (uint32_t)(((c / I8_STAGES) - 1) & 1));
+            if (c >= STAGES) mbar_wait(empty + (c % STAGES), (uint32_t)(((c / STAGES) - 1) & 1));
             issue(c);
-            if (c >= I8_LAG) {
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(I8_LAG));
-                publish(c - I8_LAG);
+            if (c >= LAG) {
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(LAG));
+                publish(c - LAG);
             }
         }
         // drain
-        if (nchunks >= 2) { asm volatile("cp.async.wait_group 1;\n" ::); publish(nchunks - 2); }
+        if (LAG >= 2 && nchunks >= 2) { asm volatile("cp.async.wait_group 1;\n" ::); publish(nchunks - 2); }
         asm volatile("cp.async.wait_group 0;\n" ::);
         if (nchunks >= 1) publish(nchunks - 1);
 
@@ -397,7 +403,8 @@ int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long l
     if (K % I8_BK != 0 || (lda % 16) || (ldb % 16) || (ldd % 4)) return 1;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(i8gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(i8gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return 2;
+        if (cudaFuncSetAttribute(i8gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM2) != cudaSuccess) return 2;
         attr_set = true;
     }
     const int mt = (M + I8_BM - 1) / I8_BM, nt = (N + I8_BN - 1) / I8_BN, nchunks = K / I8_BK;
@@ -416,7 +423,11 @@ int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long l
     }
     I8Args p{A, lda, M, B, ldb, N, K, D, ldd, cps};
     dim3 grid(mt, nt, nsplit);
-    i8gemm_kernel<<<grid, 160, I8_SMEM, st>>>(p);
+    // short contractions with many tiles: two CTAs per SM hide the per-CTA prologue and epilogue
+    const char* force = getenv("BTF_I8_STAGES");
+    const bool two = force ? (force[0] == '2') : (cps <= 64 && mt * nt * nsplit >= 2 * 148);
+    if (two) i8gemm_kernel<2><<<grid, 160, I8_SMEM2, st>>>(p);
+    else i8gemm_kernel<4><<<grid, 160, I8_SMEM, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
