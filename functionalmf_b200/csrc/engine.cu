@@ -54,10 +54,15 @@ struct btf_engine {
     btf_config cfg;
     int N, M, T, K, order, q, kd, RD, L, nco, P, Ppad, nloc, nloc_pad, n;
     int Mloc;
+    int Nall_pad;                // global row count padded to 128: contraction length of the column-sharded product block
+    int p0, Ploc;                // this rank's (j,t) range: [p0, p0 + Ploc) = [col_begin T, col_end T)
     int Kp;                      // K rounded up to the band solver's block size (8, 16, 32)
     size_t wL_stride, wy_stride; // per-column workspace strides of the band solver
     int sm_count;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};   // forked inside a sweep: tensor-core product block | HBM-bound linear block
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool overlap = true;         // BTF_NO_OVERLAP=1: everything on one stream (A/B runs)
     // state
     double *W = nullptr, *V = nullptr, *Tau2 = nullptr, *Tau2_a = nullptr, *Tau2_b = nullptr, *Tau2_c = nullptr;
     Scalars* scal = nullptr;
@@ -83,7 +88,7 @@ struct btf_engine {
     // K1 on the integer tensor cores (stats_i8.cu): decided per data set, buffers allocated on first use
     bool i8_on = false, i8_decided = false;
     StatsI8Buffers i8{};
-    uint8_t* cntT = nullptr;     // [P][nloc_pad] transposed counts (right operand of the column contraction)
+    uint8_t* cntT = nullptr;     // [Ploc][Nall_pad] counts of this rank's columns over ALL rows (right operand of the column contraction)
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
     EvalSlot eval[EVAL_SLOTS];
@@ -101,6 +106,9 @@ struct btf_engine {
     int* diag_retries = nullptr;
     // scheduling
     bool resid_valid = false;
+    bool tau_sharded = false;    // Tau2 chain updated for own columns (+ the last column) only; gathered at API boundaries
+    bool tau_stale = false;
+    int64_t eager_sweeps = 0;    // sharded engines run their first sweep eagerly (NCCL sets up its channels on first use)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_launches = 0;
     int64_t launches = 0;
@@ -198,12 +206,20 @@ int btf_create(const btf_config* c, btf_engine** out) {
     e->nloc_pad = round_up(std::max(e->nloc, 1), 128);
     e->Mloc = e->cfg.col_end - e->cfg.col_begin;
     if (e->nloc < 0 || e->Mloc < 0) { delete e; return set_err(BTF_EINVAL, "bad shard"); }
+    e->Nall_pad = e->cfg.world_size > 1 ? round_up(e->N, 128) : e->nloc_pad;
+    e->p0 = e->cfg.col_begin * e->T; e->Ploc = e->Mloc * e->T;
+    e->overlap = getenv("BTF_NO_OVERLAP") == nullptr;
     CK(cudaSetDevice(c->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&e->ph_ev[i]));
@@ -345,6 +361,11 @@ void btf_destroy(btf_engine* e) {
     if (e->ev_copied) cudaEventDestroy(e->ev_copied);
     for (int i = 0; i <= PH_COUNT; ++i) if (e->ph_ev[i]) cudaEventDestroy(e->ph_ev[i]);
     for (int i = 0; i < 6; ++i) if (e->i8_ev[i / 3][i % 3]) cudaEventDestroy(e->i8_ev[i / 3][i % 3]);
+    for (int i = 0; i < 2; ++i) {
+        if (e->side[i]) cudaStreamDestroy(e->side[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -663,21 +684,105 @@ static inline void phase_mark(btf_engine* e, int idx) {
     if (e->time_phases) cudaEventRecord(e->ph_ev[idx], e->stream);
 }
 
+// ---- K1 on the integer tensor cores, staged over the engine's streams (stats_i8.cu).
+// begin_*: digits + tensor-core product block on side[0], FP64 linear block on side[1] (or everything on the main
+// stream when `fork` is false); finish_*: join, exchange of the linear block (sharded columns), recombination.
+struct I8Pending { int product = 0, nsplit = 1; };
+
+static void fork_side(btf_engine* e, bool fork) {
+    if (!fork) return;
+    cudaEventRecord(e->ev_fork, e->stream);
+    cudaStreamWaitEvent(e->side[0], e->ev_fork, 0);
+    cudaStreamWaitEvent(e->side[1], e->ev_fork, 0);
+}
+static void join_side(btf_engine* e, bool fork) {
+    if (!fork) return;
+    for (int i = 0; i < 2; ++i) {
+        cudaEventRecord(e->ev_join[i], e->side[i]);
+        cudaStreamWaitEvent(e->stream, e->ev_join[i], 0);
+    }
+}
+
+static int begin_row_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd) {
+    cudaStream_t sa = fork ? e->side[0] : e->stream, sb = fork ? e->side[1] : e->stream;
+    cudaEvent_t* ev = (e->time_phases && timer >= 0) ? e->i8_ev[timer] : nullptr;
+    fork_side(e, fork);
+    stats_i8_digits(e->i8, e->K, e->V, e->P, e->Ppad, sa);
+    if (ev) cudaEventRecord(ev[0], sa);
+    pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, e->row_stats, sa);
+    if (pd->product != 0 && pd->product != 10) return set_err(BTF_ECUDA, "integer row statistics failed to launch");
+    if (ev) cudaEventRecord(ev[1], sa);
+    pd->nsplit = stats_i8_linear(e->i8, false, e->K, e->S, e->Ppad, e->V, e->Ppad, e->nloc, sb);
+    if (ev) cudaEventRecord(ev[2], sb);
+    e->launches += 4;
+    return BTF_OK;
+}
+static int finish_row_stats_i8(btf_engine* e, bool fork, const I8Pending& pd) {
+    join_side(e, fork);
+    stats_i8_combine(e->i8, e->K, e->nloc, e->nloc_pad, pd.product == 10, pd.nsplit, 0, e->nloc, e->row_stats, e->stream);
+    e->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? BTF_OK : set_err(BTF_ECUDA, "integer row statistics failed");
+}
+
+// Columns: every rank contracts ITS columns over ALL rows (column-sharded copy of the counts, digit planes of the
+// all-gathered W), so the product block needs no exchange; the linear block is a partial sum over the local rows
+// for all columns (S stays row-sharded: it is read once either way) and is reduce-scattered (M T K doubles).
+static int begin_col_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd) {
+    cudaStream_t sa = fork ? e->side[0] : e->stream, sb = fork ? e->side[1] : e->stream;
+    cudaEvent_t* ev = (e->time_phases && timer >= 0) ? e->i8_ev[timer] : nullptr;
+    const int nco = e->nco;
+    fork_side(e, fork);
+    pd->product = 0;
+    if (ev) cudaEventRecord(ev[0], sa);
+    if (e->Ploc > 0) {
+        stats_i8_digits(e->i8, e->K, e->W, e->N, e->Nall_pad, sa);
+        if (ev) cudaEventRecord(ev[0], sa);
+        pd->product = stats_i8_product(e->i8, e->K, e->cntT, e->Nall_pad, e->Nall_pad, e->Ploc, round_up(e->Ploc, 256),
+                                       e->col_stats + (size_t)e->p0 * nco, sa);
+        if (pd->product != 0 && pd->product != 10) return set_err(BTF_ECUDA, "integer column statistics failed to launch");
+        e->launches += 3;
+    }
+    if (ev) cudaEventRecord(ev[1], sa);
+    pd->nsplit = 1;
+    if (e->nloc > 0) {
+        pd->nsplit = stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, e->W + (size_t)e->cfg.row_begin * e->K, e->nloc_pad, e->P, sb);
+        e->launches += 1;
+    } else {
+        cudaMemsetAsync(e->i8.bpart, 0, (size_t)e->P * e->K * sizeof(double), sb);
+    }
+    if (ev) cudaEventRecord(ev[2], sb);
+    return BTF_OK;
+}
+static int finish_col_stats_i8(btf_engine* e, bool fork, const I8Pending& pd) {
+    join_side(e, fork);
+    if (e->shard && nccl_reduce_scatter_cols(e->shard, e->i8.bpart, (size_t)e->T * e->K, e->stream))
+        return set_err(BTF_ENCCL, "reduce-scatter(linear block) failed: %s", nccl_shard_error());
+    if (e->Ploc > 0) {
+        stats_i8_combine(e->i8, e->K, e->Ploc, round_up(e->Ploc, 256), pd.product == 10, pd.nsplit, e->p0, e->P,
+                         e->col_stats + (size_t)e->p0 * e->nco, e->stream);
+        e->launches += 1;
+    }
+    return cudaGetLastError() == cudaSuccess ? BTF_OK : set_err(BTF_ECUDA, "integer column statistics failed");
+}
+
 // The integer-tensor-core statistics path: Gaussian data (count weights), K in {8, 16, 32}, accumulators
 // that cannot overflow, and a tensor large enough for the digit planes to pay (BTF_STATS_FORCE_I8=1
-// forces it for any size, BTF_STATS_NO_I8=1 disables it).
+// forces it for any size, BTF_STATS_NO_I8=1 disables it).  The decision only uses global quantities, so
+// every rank of a sharded engine takes the same path (the two paths exchange different things).
 static int ensure_i8(btf_engine* e) {
     if (e->i8_decided) return BTF_OK;
     e->i8_decided = true;
     e->i8_on = false;
     if (e->cfg.likelihood != BTF_GAUSSIAN || !e->has_data) return BTF_OK;
     const bool force = getenv("BTF_STATS_FORCE_I8") != nullptr;
-    const long long cells = (long long)e->nloc * e->P;
-    if (!stats_i8_supported(e->K, e->nreps, e->Ppad, e->nloc_pad) || e->nloc < 1) return BTF_OK;
+    const long long cells = (long long)e->N * e->P / std::max(1, e->cfg.world_size);
+    if (!stats_i8_supported(e->K, e->nreps, e->Ppad, e->Nall_pad)) return BTF_OK;
+    if (e->cfg.world_size > 1 && !e->shard) return BTF_OK;       // a shard without a communicator cannot build its column copy
     if (!force && cells < (1ll << 24)) return BTF_OK;
+    cudaStream_t st = e->stream;
     if (!e->i8.planes) {
         StatsI8Sizes z;
-        stats_i8_sizes(e->K, e->nloc_pad, e->Ppad, e->nloc, e->P, &z);
+        stats_i8_sizes(e->K, e->nloc_pad, e->Ppad, e->nloc, e->P, e->Nall_pad, e->Ploc, &z);
         CK(cudaMalloc((void**)&e->i8.planes, z.planes_bytes));
         CK(cudaMemset(e->i8.planes, 0, z.planes_bytes));
         CK(dev_alloc(&e->i8.colmax, (size_t)z.L));
@@ -687,17 +792,35 @@ static int ensure_i8(btf_engine* e) {
         CK(dev_alloc(&e->cntT, z.cntT_bytes));
         e->i8.nsplit_b_row = z.nsplit_b_row;
     }
-    launch_transpose_u8(e->cnt, e->Ppad, e->nloc, e->P, e->cntT, e->nloc_pad, e->stream);
-    e->launches++;
+    if (!e->shard) {
+        launch_transpose_u8(e->cnt, e->Ppad, e->nloc, e->P, e->cntT, e->Nall_pad, st);
+        e->launches++;
+    } else {
+        // transpose the local row block, then exchange: every rank keeps the counts of ITS columns over all rows
+        uint8_t *tT = nullptr, *tmp = nullptr;
+        const size_t tbytes = (size_t)e->P * e->nloc_pad;
+        const size_t rbytes = (size_t)std::max(e->Ploc, 1) * round_up(std::max(nccl_shard_max_rows(e->shard), 1), 128);
+        CK(cudaMalloc((void**)&tT, std::max<size_t>(tbytes, 1)));
+        if (cudaMalloc((void**)&tmp, rbytes) != cudaSuccess) { cudaFree(tT); return set_err(BTF_ECUDA, "out of memory for the count exchange"); }
+        cudaMemsetAsync(tT, 0, std::max<size_t>(tbytes, 1), st);
+        cudaMemsetAsync(e->cntT, 0, (size_t)std::max(e->Ploc, 1) * e->Nall_pad, st);
+        if (e->nloc > 0) { launch_transpose_u8(e->cnt, e->Ppad, e->nloc, e->P, tT, e->nloc_pad, st); e->launches++; }
+        const int rc = nccl_exchange_counts(e->shard, tT, e->nloc_pad, e->T, e->cntT, e->Nall_pad, tmp, st);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        cudaFree(tT); cudaFree(tmp);
+        if (rc) return set_err(BTF_ENCCL, "exchange of the count blocks failed: %s", nccl_shard_error());
+        if (ce != cudaSuccess) return set_err(BTF_ECUDA, "exchange of the count blocks: %s", cudaGetErrorString(ce));
+    }
     // one eager pass so that every kernel attribute is set before a graph capture
-    if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
-                        e->row_stats, e->stream))
-        return set_err(BTF_ECUDA, "integer statistics path failed to launch");
-    if (launch_stats_i8(e->i8, true, e->K, e->cntT, e->nloc_pad, e->S, e->Ppad, e->W + (size_t)e->cfg.row_begin * e->K,
-                        e->nloc, e->nloc_pad, e->P, e->Ppad, e->col_stats, e->stream))
-        return set_err(BTF_ECUDA, "integer statistics path failed to launch");
-    CK(cudaStreamSynchronize(e->stream));
     e->i8_on = true;
+    I8Pending pd;
+    if (e->nloc > 0) {
+        int rc = begin_row_stats_i8(e, false, -1, &pd); if (rc) { e->i8_on = false; return rc; }
+        rc = finish_row_stats_i8(e, false, pd); if (rc) { e->i8_on = false; return rc; }
+    }
+    { int rc = begin_col_stats_i8(e, false, -1, &pd); if (rc) { e->i8_on = false; return rc; }
+      rc = finish_col_stats_i8(e, false, pd); if (rc) { e->i8_on = false; return rc; } }
+    CK(cudaStreamSynchronize(st));
     free_graph(e);
     return BTF_OK;
 }
@@ -722,6 +845,12 @@ static int enqueue_sweep(btf_engine* e) {
     const int mask = c.sample_mask;
     launch_bump_sweep(e->scal, st); e->launches++;
     phase_mark(e, PH_NU2);
+    // Integer statistics path: the row statistics only read V and the data, so they start now on the side streams
+    // (tensor-core product block | HBM-bound linear block) while the hyper-parameter steps run on the main stream.
+    const bool doW = (mask & BTF_SAMPLE_W) && e->nloc > 0;
+    const bool fork = e->overlap && e->i8_on && !e->time_phases;
+    I8Pending pend_row, pend_col;
+    if (fork && doW) { int rc = begin_row_stats_i8(e, true, 0, &pend_row); if (rc) return rc; }
 
     if (c.likelihood == BTF_NEGBINOMIAL) {
         NbArgs nb;
@@ -779,8 +908,21 @@ static int enqueue_sweep(btf_engine* e) {
     ha.d_start = e->d_start; ha.d_width = e->d_width; ha.d_coef = e->d_coef; ha.d_maxw = e->d_maxw;
     ha.Tau2 = e->Tau2; ha.Tau2_a = e->Tau2_a; ha.Tau2_b = e->Tau2_b; ha.Tau2_c = e->Tau2_c;
     ha.stability = c.stability; ha.g_inject = inj(e, "g_tau"); ha.seed = c.seed;
-    ha.lam_partials = nullptr; ha.col_begin = 0; ha.col_end = e->M;   // replicated on every rank (Philox is keyed by (j, r))
-    if (mask & BTF_SAMPLE_TAU2) { launch_tau2(ha, st); e->launches++; }
+    ha.lam_partials = nullptr; ha.col_begin = 0; ha.col_end = e->M;   // Philox is keyed by (j, r): identical on every rank
+    if (mask & BTF_SAMPLE_TAU2) {
+        if (e->tau_sharded) {
+            // own columns only (the band solve needs no others); the reference's lam2 step reads the LAST column
+            // (factor.py:150), which every rank therefore updates too; the blocks are gathered at API boundaries
+            HyperArgs hs = ha;
+            hs.col_begin = c.col_begin; hs.col_end = c.col_end;
+            launch_tau2(hs, st);
+            if (c.col_end != e->M) { hs.col_begin = e->M - 1; hs.col_end = e->M; launch_tau2(hs, st); e->launches++; }
+            e->tau_stale = true;
+        } else {
+            launch_tau2(ha, st);
+        }
+        e->launches++;
+    }
     phase_mark(e, PH_LAM2);
     if (mask & BTF_SAMPLE_LAM2) {
         HyperArgs hl = ha;
@@ -795,13 +937,10 @@ static int enqueue_sweep(btf_engine* e) {
     // ---- W | rest
     phase_mark(e, PH_ROW_STATS);
     const void* wt = gauss ? (const void*)e->cnt : (const void*)e->omega;
-    if ((mask & BTF_SAMPLE_W) && e->nloc > 0) {
+    if (doW) {
         if (e->i8_on) {
-            for (int q = 0; q < 3; ++q) e->i8.ev[q] = e->time_phases ? e->i8_ev[0][q] : nullptr;
-            if (launch_stats_i8(e->i8, false, e->K, e->cnt, e->Ppad, e->S, e->Ppad, e->V, e->P, e->Ppad, e->nloc, e->nloc_pad,
-                                e->row_stats, st))
-                return set_err(BTF_ECUDA, "integer row statistics failed to launch");
-            e->launches += 5;
+            if (!fork) { int rc = begin_row_stats_i8(e, false, 0, &pend_row); if (rc) return rc; }
+            { int rc = finish_row_stats_i8(e, fork, pend_row); if (rc) return rc; }
         } else {
             launch_stats(e->plan_row, false, !gauss, wt, e->S, e->V, e->Ppad, e->Ppad, e->nloc, e->row_stats, e->zbuf, st);
             e->launches += e->plan_row.zpre ? 2 : 1;
@@ -829,33 +968,31 @@ static int enqueue_sweep(btf_engine* e) {
     if (mask & BTF_SAMPLE_V) {
         int nsplit = e->plan_col.nsplit;
         if (e->i8_on) {
-            for (int q = 0; q < 3; ++q) e->i8.ev[q] = e->time_phases ? e->i8_ev[1][q] : nullptr;
-            if (launch_stats_i8(e->i8, true, e->K, e->cntT, e->nloc_pad, e->S, e->Ppad, e->W + (size_t)c.row_begin * e->K,
-                                e->nloc, e->nloc_pad, e->P, e->Ppad, e->col_stats, st))
-                return set_err(BTF_ECUDA, "integer column statistics failed to launch");
-            e->launches += 5;
+            { int rc = begin_col_stats_i8(e, fork, 1, &pend_col); if (rc) return rc; }
+            { int rc = finish_col_stats_i8(e, fork, pend_col); if (rc) return rc; }
             nsplit = 1;
+            e->col_collapsed = false;
         } else {
             launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->nloc_pad, e->Ppad, e->P,
                          e->col_stats, e->zbuf, st);
             e->launches += e->plan_col.zpre ? 2 : 1;
-        }
-        if (e->shard) {
-            // sum the split partials locally is folded into the band kernel only on one GPU; across GPUs the
-            // partial statistics are first collapsed over splits, then reduce-scattered by column block
-            if (nccl_reduce_col_stats(e->shard, e->col_stats, nsplit, e->plan_col.out_elems_per_split, e->T * e->nco, st))
-                return set_err(BTF_ENCCL, "reduce-scatter(col stats) failed");
-            nsplit = 1;
-            e->col_collapsed = true;
-        } else if (nsplit > 2) {
-            // deep split-K (few columns): one pass that sums the partials in split order, instead of
-            // nsplit dependent loads per statistic inside the latency-bound band kernel
-            launch_collapse_splits(e->col_stats, nsplit, e->plan_col.out_elems_per_split, st);
-            e->launches++;
-            nsplit = 1;
-            e->col_collapsed = true;
-        } else {
-            e->col_collapsed = false;
+            if (e->shard) {
+                // FP64 statistics path across GPUs: partial statistics over the local rows for all columns, collapsed
+                // over the splits, then reduce-scattered by column block
+                if (nccl_reduce_col_stats(e->shard, e->col_stats, nsplit, e->plan_col.out_elems_per_split, e->T * e->nco, st))
+                    return set_err(BTF_ENCCL, "reduce-scatter(col stats) failed");
+                nsplit = 1;
+                e->col_collapsed = true;
+            } else if (nsplit > 2) {
+                // deep split-K (few columns): one pass that sums the partials in split order, instead of
+                // nsplit dependent loads per statistic inside the latency-bound band kernel
+                launch_collapse_splits(e->col_stats, nsplit, e->plan_col.out_elems_per_split, st);
+                e->launches++;
+                nsplit = 1;
+                e->col_collapsed = true;
+            } else {
+                e->col_collapsed = false;
+            }
         }
         phase_mark(e, PH_BAND_SOLVE);
         if (e->Mloc > 0) {
@@ -897,6 +1034,16 @@ static int enqueue_sweep(btf_engine* e) {
     return BTF_OK;
 }
 
+// Sharded engines update the Tau2 chain for their own columns only: make the four arrays whole again
+// (every rank calls the same API sequence, so the collectives match).
+static int sync_tau(btf_engine* e) {
+    if (!e->shard || !e->tau_stale) return BTF_OK;
+    double* arrs[4] = {e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c};
+    if (nccl_allgather_tau(e->shard, arrs, 4, e->RD, e->stream)) return set_err(BTF_ENCCL, "all-gather(Tau2) failed: %s", nccl_shard_error());
+    e->tau_stale = false;
+    return BTF_OK;
+}
+
 static int check_info(btf_engine* e) {
     CK(cudaMemcpyAsync(e->pinned_scal, e->scal, sizeof(Scalars), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -909,7 +1056,9 @@ static int check_info(btf_engine* e) {
 }
 
 static bool graph_ok(btf_engine* e) {
-    return e->cfg.use_graph && !e->shard && e->inject.empty() && !e->diag && !e->time_phases &&
+    // (sharded engines: the NCCL collectives are captured with the kernels; the first sweep runs eagerly
+    //  so that NCCL has set up its channels before a capture)
+    return e->cfg.use_graph && (!e->shard || e->eager_sweeps > 0) && e->inject.empty() && !e->diag && !e->time_phases &&
            (e->resid_valid || e->cfg.likelihood != BTF_GAUSSIAN || e->cfg.resid_direct || !(e->cfg.sample_mask & BTF_SAMPLE_NU2));
 }
 
@@ -938,6 +1087,7 @@ static int one_sweep(btf_engine* e) {
         return BTF_OK;
     }
     int rc = enqueue_sweep(e);
+    e->eager_sweeps++;
     if (!e->inject.empty()) {
         // injected noise is consumed by exactly one sweep
         CK(cudaStreamSynchronize(e->stream));
@@ -963,6 +1113,8 @@ int btf_sweep(btf_engine* e, int32_t nsweeps) {
     int rc = pre_run(e);
     if (rc) return rc;
     for (int s = 0; s < nsweeps; ++s) { rc = one_sweep(e); if (rc) return rc; }
+    rc = sync_tau(e);
+    if (rc) return rc;
     return check_info(e);
 }
 
@@ -980,6 +1132,8 @@ int btf_sweep_timed(btf_engine* e, int32_t nsweeps, double* ms_out) {
     CK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     if (ms_out) *ms_out = ms;
+    if (rc) return rc;
+    rc = sync_tau(e);
     if (rc) return rc;
     return check_info(e);
 }
@@ -1014,6 +1168,8 @@ int btf_time_phases(btf_engine* e, int32_t nsweeps, double* ms_out, int32_t npha
     }
     e->time_phases = false;
     for (int i = 0; i < nphases; ++i) ms_out[i] /= std::max(1, nsweeps);
+    if (rc) return rc;
+    rc = sync_tau(e);
     if (rc) return rc;
     return check_info(e);
 }
@@ -1058,6 +1214,7 @@ int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t 
             for (int sl = 0; sl < EVAL_SLOTS; ++sl)
                 if (e->eval[sl].active && e->eval[sl].auto_update) { rc = eval_enqueue(e, sl); if (rc) return rc; }
             // snapshot on the compute stream (device-to-device), drain on the copy stream
+            if (Tau2_out) { rc = sync_tau(e); if (rc) return rc; }
             if (pending) CK(cudaStreamWaitEvent(e->stream, e->ev_copied, 0));
             if (W_out) CK(cudaMemcpyAsync(e->snapW, e->W, wn * 8, cudaMemcpyDeviceToDevice, e->stream));
             if (V_out) CK(cudaMemcpyAsync(e->snapV, e->V, vn * 8, cudaMemcpyDeviceToDevice, e->stream));
@@ -1081,6 +1238,8 @@ int btf_run_segment(btf_engine* e, int32_t nsweeps, int32_t first_save, int32_t 
         }
     }
     CK(cudaStreamSynchronize(e->copy_stream));
+    rc = sync_tau(e);
+    if (rc) return rc;
     return check_info(e);
 }
 
@@ -1347,5 +1506,8 @@ int btf_nccl_init(btf_engine* e, const char* id128) {
     e->shard = nccl_shard_create(id128, e->cfg.world_size, e->cfg.rank, e->N, e->M, e->cfg.row_begin, e->cfg.row_end,
                                  e->cfg.col_begin, e->cfg.col_end);
     if (!e->shard) return set_err(BTF_ENCCL, "NCCL init failed: %s", nccl_shard_error());
+    // the lam2 step in its all-columns form needs every column's new Tau2: keep the chain replicated there
+    e->tau_sharded = e->cfg.ref_compat_lam2 != 0 && getenv("BTF_TAU_REPLICATED") == nullptr;
+    e->i8_decided = false;
     return BTF_OK;
 }

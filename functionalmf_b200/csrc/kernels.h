@@ -54,9 +54,18 @@ struct StatsI8Buffers {
     cudaEvent_t ev[3];              // optional timers: before the GEMM, after the GEMM, after the linear block (null: off)
 };
 bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col);
-void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes* s);
+// nall_pad: padded GLOBAL row count (contraction length of the column side), ploc: columns (j,t) owned by this rank
+void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, int nall_pad, int ploc, StatsI8Sizes* s);
 void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, uint8_t* dst, long long ldd, cudaStream_t st);
-// out[m][L+K] (one split) for count weights: exact product block + FP64 linear block
+// the four stages of the integer path (engine: tensor-core contraction and HBM-bound linear block on separate streams)
+void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows, int kdim_pad, cudaStream_t st);
+int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
+                     double* out, cudaStream_t st);     // 0: int32 planes in w.D, 10: fused epilogue wrote out, else error
+int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S, long long lds, const double* F,
+                    int kdim_pad, int m_valid, cudaStream_t st);     // returns the split count of w.bpart
+void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, bool product_done, int nsplit_b,
+                      long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st);
+// out[m][L+K] (one split) for count weights: exact product block + FP64 linear block, all stages on one stream
 int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
                     long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,
                     cudaStream_t st);

@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace btf {
@@ -10,7 +11,7 @@ namespace btf {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclInt32 = 2, ncclFloat64 = 8 };
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 
 struct NcclApi {
@@ -23,6 +24,8 @@ struct NcclApi {
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -48,6 +51,8 @@ static bool load_api() {
     SYM(Reduce, "ncclReduce")
     SYM(ReduceScatter, "ncclReduceScatter")
     SYM(Broadcast, "ncclBroadcast")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -180,6 +185,72 @@ int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t sp
         NC(g_api.Reduce(p, p, cnt, ncclFloat64, ncclSum, r, s->comm, st));
     }
     NC(g_api.GroupEnd());
+    return 0;
+}
+
+// in-place sum of a per-(j,t) array [M * T][unit] across ranks; afterwards every rank holds the totals of ITS column block
+int nccl_reduce_scatter_cols(NcclShard* s, double* buf, size_t per_col_elems, cudaStream_t st) {
+    if (s->uniform_cols) {
+        const size_t cnt = (size_t)(s->ce[0] - s->cb[0]) * per_col_elems;
+        NC(g_api.ReduceScatter(buf, buf + (size_t)s->rank * cnt, cnt, ncclFloat64, ncclSum, s->comm, st));
+        return 0;
+    }
+    NC(g_api.GroupStart());
+    for (int r = 0; r < s->world; ++r) {
+        size_t cnt = (size_t)(s->ce[r] - s->cb[r]) * per_col_elems;
+        if (cnt == 0) continue;
+        double* p = buf + (size_t)s->cb[r] * per_col_elems;
+        NC(g_api.Reduce(p, p, cnt, ncclFloat64, ncclSum, r, s->comm, st));
+    }
+    NC(g_api.GroupEnd());
+    return 0;
+}
+
+// the four Tau2 arrays [M][RD], column blocks gathered in place
+int nccl_allgather_tau(NcclShard* s, double* const* arrays, int narr, int RD, cudaStream_t st) {
+    for (int a = 0; a < narr; ++a)
+        if (gather_blocks(s, arrays[a], s->cb, s->ce, (size_t)RD, st, s->uniform_cols)) return -1;
+    return 0;
+}
+
+int nccl_shard_max_rows(const NcclShard* s) {
+    int m = 0;
+    for (int r = 0; r < s->world; ++r) m = std::max(m, s->re[r] - s->rb[r]);
+    return m;
+}
+
+// Column-sharded copy of the counts: dst[p - p0][i] = cnt[i][p] for this rank's columns p in [p0, p1) = [cb T, ce T) and
+// ALL rows i.  Every rank holds srcT = transpose of its own row block, [P][src_ld]; the (rank, peer) blocks move in
+// world rounds of one send + one receive (contiguous row ranges of srcT), then a strided copy puts the block in place.
+// tmp: >= (p1 - p0) * round_up(max rows per rank, 128) bytes.
+int nccl_exchange_counts(NcclShard* s, const uint8_t* srcT, long long src_ld, int T, uint8_t* dst, long long dst_ld,
+                         uint8_t* tmp, cudaStream_t st) {
+    const int me = s->rank, W = s->world;
+    const size_t ploc = (size_t)(s->ce[me] - s->cb[me]) * T;
+    auto pad128 = [](int x) { return (long long)((x + 127) / 128 * 128); };
+    for (int r = 0; r < W; ++r) {
+        const int to = (me + r) % W, from = (me - r + W) % W;
+        const long long from_ld = pad128(s->re[from] - s->rb[from]);
+        const size_t send_bytes = (size_t)(s->ce[to] - s->cb[to]) * T * (size_t)src_ld;
+        const size_t recv_bytes = ploc * (size_t)from_ld;
+        const uint8_t* block = tmp;
+        if (r == 0) {
+            block = srcT + (size_t)s->cb[me] * T * (size_t)src_ld;
+        } else {
+            NC(g_api.GroupStart());
+            if (send_bytes) NC(g_api.Send(srcT + (size_t)s->cb[to] * T * (size_t)src_ld, send_bytes, ncclUint8, to, s->comm, st));
+            if (recv_bytes) NC(g_api.Recv(tmp, recv_bytes, ncclUint8, from, s->comm, st));
+            NC(g_api.GroupEnd());
+        }
+        const size_t width = (size_t)(s->re[from] - s->rb[from]);
+        if (ploc && width) {
+            if (cudaMemcpy2DAsync(dst + s->rb[from], (size_t)dst_ld, block, (size_t)from_ld, width, ploc,
+                                  cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+                snprintf(g_nccl_err, sizeof(g_nccl_err), "strided copy of a count block failed");
+                return -1;
+            }
+        }
+    }
     return 0;
 }
 

@@ -27,6 +27,14 @@ void launch_collapse_splits(double* x, int nsplit, size_t stride, cudaStream_t s
 int nccl_reduce_col_stats(NcclShard* s, double* col_stats, int nsplit, size_t split_stride, int per_col_elems,
                           cudaStream_t st);
 int nccl_allreduce_sum(NcclShard* s, double* p, int n, cudaStream_t st);
+// in-place sum across ranks of a per-(j,t) array [M * T][per_col_elems / T ...]: rank r ends up with the totals of its column block
+int nccl_reduce_scatter_cols(NcclShard* s, double* buf, size_t per_col_elems, cudaStream_t st);
+// in-place all-gather of the column blocks of `narr` arrays [M][RD] (the Tau2 chain)
+int nccl_allgather_tau(NcclShard* s, double* const* arrays, int narr, int RD, cudaStream_t st);
+int nccl_shard_max_rows(const NcclShard* s);
+// column-sharded copy of the uint8 counts (see nccl_shard.cu)
+int nccl_exchange_counts(NcclShard* s, const uint8_t* srcT, long long src_ld, int T, uint8_t* dst, long long dst_ld,
+                         uint8_t* tmp, cudaStream_t st);
 // scal->resid currently holds ss_total + (local partial); make it ss_total + sum of all partials
 int nccl_allreduce_resid(NcclShard* s, Scalars* scal, cudaStream_t st);
 

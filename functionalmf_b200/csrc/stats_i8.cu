@@ -113,81 +113,90 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
 }
 
 // out[split][m][j] = sum_k S[m,k] F[k,j] over the split's k range: FP64 tensor pipe, HBM bound.
-// 128 rows x 32 contraction elements per stage; a warp owns 16 rows x all columns = 2 CT independent
+// 128 rows x KC contraction elements per stage, NST stages; a warp owns 16 rows x all columns = 2 CT independent
 // accumulator chains (the FP64 mma has a long latency: two chains left the pipe 40 % idle).
-template <int KB, bool TRANS>
-__global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ F,
-                                                    int K, int m_valid, int nchunks, int chunks_per_split,
-                                                    double* __restrict__ out) {
-    constexpr int BM = 128, KC = 32, FS = KB + 4, CT = KB / 8;
+// Work items (row tile, split) are dealt round-robin to the CTAs of the grid: one item per CTA in the classic
+// launch (KC = 32, two stages, two CTAs per SM), several in the co-resident launch (KC = 16, three stages, ONE CTA
+// per SM with < 77 KB of shared memory, so that it shares every SM with one CTA of the int8 GEMM).
+template <int KB, bool TRANS, int KC, int NST, int MINB>
+__global__ void __launch_bounds__(256, MINB) sf_kernel(const double* __restrict__ S, long long lds, const double* __restrict__ F,
+                                                       int K, int m_valid, int nchunks, int chunks_per_split, int m_tiles,
+                                                       int nitems, double* __restrict__ out) {
+    constexpr int BM = 128, FS = KB + 4, CT = KB / 8;
     constexpr int SROWS = TRANS ? KC : BM, SCOLS = TRANS ? BM : KC, SS = SCOLS + 4;   // strides = 4 (mod 16) doubles
     extern __shared__ __align__(16) double smf[];
-    double* Ssm = smf;                       // [2][SROWS][SS]   (!TRANS: [m][k], TRANS: [k][m])
-    double* Fsm = smf + 2 * SROWS * SS;      // [2][KC][FS]
+    double* Ssm = smf;                         // [NST][SROWS][SS]   (!TRANS: [m][k], TRANS: [k][m])
+    double* Fsm = smf + NST * SROWS * SS;      // [NST][KC][FS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * BM;
-    const int c_begin = blockIdx.y * chunks_per_split, c_end = min(nchunks, c_begin + chunks_per_split);
-    auto load = [&](int stage, int chunk) {
-        const long long k0 = (long long)chunk * KC;
-        double* sd = Ssm + stage * SROWS * SS;
-        constexpr int CPR = SCOLS / 2;       // 16-byte copies per row
-        for (int e = tid; e < SROWS * CPR; e += 256) {
-            const int r = e / CPR, q = e - r * CPR;
-            const double* src = TRANS ? S + (k0 + r) * lds + m0 + 2 * q : S + (long long)(m0 + r) * lds + k0 + 2 * q;
-            cp_async16(sd + r * SS + 2 * q, src);
-        }
-        double* fd = Fsm + stage * KC * FS;
-        for (int e = tid; e < KC * K / 2; e += 256) {
-            const int r = (2 * e) / K, cidx = (2 * e) - r * K;
-            cp_async16(fd + r * FS + cidx, F + (k0 + r) * K + cidx);
-        }
-    };
-    double acc[2][CT][2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
     // zero the padding columns of the F tiles once (K < KB)
-    for (int e = tid; e < 2 * KC * FS; e += 256) Fsm[e] = 0.0;
+    for (int e = tid; e < NST * KC * FS; e += 256) Fsm[e] = 0.0;
     __syncthreads();
-    if (c_begin < c_end) load(0, c_begin);
-    cp_async_commit();
-    for (int c = c_begin; c < c_end; ++c) {
-        const int stg = (c - c_begin) & 1;
-        if (c + 1 < c_end) load(stg ^ 1, c + 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-        const double* sd = Ssm + stg * SROWS * SS;
-        const double* fd = Fsm + stg * KC * FS;
-        const int ml = warp * 16 + (lane >> 2);
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
-            const int kl = kk * 4 + (lane & 3);
-            const double a0 = TRANS ? sd[kl * SS + ml] : sd[ml * SS + kl];
-            const double a1 = TRANS ? sd[kl * SS + ml + 8] : sd[(ml + 8) * SS + kl];
-#pragma unroll
-            for (int ct = 0; ct < CT; ++ct) {
-                const double bv = fd[kl * FS + ct * 8 + (lane >> 2)];
-                dmma(acc[0][ct][0], acc[0][ct][1], a0, bv);
-                dmma(acc[1][ct][0], acc[1][ct][1], a1, bv);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int mt = item % m_tiles, sp = item / m_tiles;
+        const int m0 = mt * BM;
+        const int c_begin = sp * chunks_per_split, c_end = min(nchunks, c_begin + chunks_per_split);
+        auto load = [&](int stage, int chunk) {
+            const long long k0 = (long long)chunk * KC;
+            double* sd = Ssm + stage * SROWS * SS;
+            constexpr int CPR = SCOLS / 2;       // 16-byte copies per row
+            for (int e = tid; e < SROWS * CPR; e += 256) {
+                const int r = e / CPR, q = e - r * CPR;
+                const double* src = TRANS ? S + (k0 + r) * lds + m0 + 2 * q : S + (long long)(m0 + r) * lds + k0 + 2 * q;
+                cp_async16(sd + r * SS + 2 * q, src);
             }
+            double* fd = Fsm + stage * KC * FS;
+            for (int e = tid; e < KC * K / 2; e += 256) {
+                const int r = (2 * e) / K, cidx = (2 * e) - r * K;
+                cp_async16(fd + r * FS + cidx, F + (k0 + r) * K + cidx);
+            }
+        };
+        double acc[2][CT][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+#pragma unroll
+        for (int s0 = 0; s0 < NST - 1; ++s0) {
+            if (c_begin + s0 < c_end) load(s0, c_begin + s0);
+            cp_async_commit();
         }
-        __syncthreads();
-    }
-    cp_async_wait<0>();
+        for (int c = c_begin; c < c_end; ++c) {
+            const int stg = (c - c_begin) % NST;
+            if (c + NST - 1 < c_end) load((c - c_begin + NST - 1) % NST, c + NST - 1);
+            cp_async_commit();
+            cp_async_wait<NST - 1>();
+            __syncthreads();
+            const double* sd = Ssm + stg * SROWS * SS;
+            const double* fd = Fsm + stg * KC * FS;
+            const int ml = warp * 16 + (lane >> 2);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int m = m0 + warp * 16 + r * 8 + (lane >> 2);
-        if (m < m_valid) {
-            double* o = out + ((long long)blockIdx.y * m_valid + m) * K;
+            for (int kk = 0; kk < KC / 4; ++kk) {
+                const int kl = kk * 4 + (lane & 3);
+                const double a0 = TRANS ? sd[kl * SS + ml] : sd[ml * SS + kl];
+                const double a1 = TRANS ? sd[kl * SS + ml + 8] : sd[(ml + 8) * SS + kl];
 #pragma unroll
-            for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = ct * 8 + (lane & 3) * 2 + h;
-                    if (j < K) o[j] = acc[r][ct][h];
+                for (int ct = 0; ct < CT; ++ct) {
+                    const double bv = fd[kl * FS + ct * 8 + (lane >> 2)];
+                    dmma(acc[0][ct][0], acc[0][ct][1], a0, bv);
+                    dmma(acc[1][ct][0], acc[1][ct][1], a1, bv);
                 }
+            }
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int m = m0 + warp * 16 + r * 8 + (lane >> 2);
+            if (m < m_valid) {
+                double* o = out + ((long long)sp * m_valid + m) * K;
+#pragma unroll
+                for (int ct = 0; ct < CT; ++ct)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = ct * 8 + (lane & 3) * 2 + h;
+                        if (j < K) o[j] = acc[r][ct][h];
+                    }
+            }
         }
     }
 }
@@ -196,7 +205,8 @@ __global__ void __launch_bounds__(256, 2) sf_kernel(const double* __restrict__ S
 // out[m][L + j] = sum_split bpart[split][m][j]
 __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restrict__ D, long long ldn, const int* __restrict__ expo,
                                                          const double* __restrict__ bpart, int nsplit_b, int m_valid, int L,
-                                                         int K, double* __restrict__ out, int first_cy) {
+                                                         int K, double* __restrict__ out, int first_cy,
+                                                         long long bpart_m0, long long bpart_rows) {
     __shared__ double tile[32][33];
     const int nco = L + K;
     const int m0 = blockIdx.x * 32, c0 = (blockIdx.y + first_cy) * 32;
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
             const int m = m0 + e / K, j = e % K;
             if (m < m_valid) {
                 double s = 0.0;
-                for (int sp = 0; sp < nsplit_b; ++sp) s += bpart[((long long)sp * m_valid + m) * K + j];
+                for (int sp = 0; sp < nsplit_b; ++sp) s += bpart[((long long)sp * bpart_rows + bpart_m0 + m) * K + j];
                 out[(long long)m * nco + L + j] = s;
             }
         }
@@ -251,15 +261,24 @@ __global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t* __rest
     }
 }
 
-template <int KB, bool TRANS>
-void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks,
-                 int nsplit, double* out, cudaStream_t st) {
-    const size_t smem = (size_t)(2 * (TRANS ? 32 * 132 : 128 * 36) + 2 * 32 * (KB + 4)) * sizeof(double);
-    auto kern = sf_kernel<KB, TRANS>;
+template <int KB, bool TRANS, int KC, int NST, int MINB>
+void launch_sf_cfg(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks,
+                   int nsplit, int grid, double* out, cudaStream_t st) {
+    const size_t smem = (size_t)(NST * (TRANS ? KC * 132 : 128 * (KC + 4)) + NST * KC * (KB + 4)) * sizeof(double);
+    auto kern = sf_kernel<KB, TRANS, KC, NST, MINB>;
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
     const int cps = (nchunks + nsplit - 1) / nsplit;
-    kern<<<dim3(m_tiles, nsplit), 256, smem, st>>>(S, lds, F, K, m_valid, nchunks, cps, out);
+    const int nitems = m_tiles * nsplit;
+    kern<<<grid > 0 ? std::min(grid, nitems) : nitems, 256, smem, st>>>(S, lds, F, K, m_valid, nchunks, cps, m_tiles, nitems, out);
+}
+
+// resident = true: the co-resident configuration (one 3-stage CTA per SM, contraction chunks of 16, `grid` CTAs)
+template <int KB, bool TRANS>
+void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks32,
+                 int nsplit, bool resident, int grid, double* out, cudaStream_t st) {
+    if (resident) launch_sf_cfg<KB, TRANS, 16, 3, 1>(S, lds, F, K, m_valid, m_tiles, nchunks32 * 2, nsplit, grid, out, st);
+    else launch_sf_cfg<KB, TRANS, 32, 2, 2>(S, lds, F, K, m_valid, m_tiles, nchunks32, nsplit, 0, out, st);
 }
 
 }  // namespace
@@ -272,12 +291,13 @@ bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col
     return kd * nreps * 64 < (1ll << 31);           // the int32 accumulators cannot overflow
 }
 
-void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, StatsI8Sizes* s) {
+void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, int nall_pad, int ploc, StatsI8Sizes* s) {
     const long long L = (long long)K * (K + 1) / 2;
-    const long long kd = std::max(nloc_pad, Ppad), nd = std::max(nloc_pad, Ppad);
+    const long long kd = std::max(nall_pad, Ppad);                          // contraction lengths: rows over p, columns over ALL rows
+    const long long nd = std::max<long long>(nloc_pad, (ploc + 255) / 256 * 256);   // output rows: local rows / local columns
     s->planes_bytes = (size_t)(NPLANES * L * kd);
     s->d_elems = (size_t)(NPLANES * L * nd);
-    s->cntT_bytes = (size_t)P * nloc_pad;
+    s->cntT_bytes = (size_t)std::max(ploc, 1) * nall_pad;
     s->nsplit_b_row = 64;            // upper bound of the split count of the row-variant linear block (buffer size)
     s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)P * K);
     s->L = (int)L;
@@ -287,56 +307,92 @@ void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, 
     transpose_u8_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
 }
 
+// ---- the integer path in stages, so that the engine can put the tensor-core contraction and the HBM-bound
+// linear block on different streams (they use disjoint resources) and shard the column side by columns.
+//
+// 1. column scales and digit planes of Z = [F (x) F packed]: planes [8 L][kdim_pad]
+void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows, int kdim_pad, cudaStream_t st) {
+    const int L = K * (K + 1) / 2;
+    cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
+    zmax_kernel<<<(f_rows + 127) / 128, 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
+    const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
+    static size_t zs_set = 0;
+    if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
+    zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, (long long)kdim_pad);
+}
+
+// 2. exact product block on the tensor cores: D[(8 c + s)][m] = sum_k d_s[k, c] B[m][k], m < m_valid (B = counts, K-major)
+//    returns 0 (int32 planes in w.D), 10 (fused epilogue wrote out[m][c] directly), else an error
+int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
+                     double* out, cudaStream_t st) {
+    const int L = K * (K + 1) / 2;
+    const bool force_fused = getenv("BTF_STATS_I8_FUSED") != nullptr && getenv("BTF_STATS_I8_NOFUSED") == nullptr;
+    // (measured on C2: the fused epilogue's FP64 stores are not hidden under the next tile, 0.29 + 0.50 ms against
+    //  0.27 + 0.35 ms + 0.08 ms of recombination, so the int32 route is the default and the fused one is opt-in)
+    if (force_fused) {
+        const int rc = launch_i8gemm_fused(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, kdim_pad, L, kdim_pad,
+                                           w.expo, out, L + K, 0, st);
+        if (rc == 0) return 10;
+        if (rc > 1) return 1;
+    }
+    return launch_i8gemm(w.planes, kdim_pad, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, m_pad, st)
+               ? 1 : 0;
+}
+
+// 3. linear block in FP64: bpart[split][m][j] = sum_k S[m, k] F[k, j] over the split's k range; returns the split count
+int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S, long long lds, const double* F,
+                    int kdim_pad, int m_valid, cudaStream_t st) {
+    const int nchunks = kdim_pad / 32;
+    const int m_tiles = (m_valid + 127) / 128;
+    // BTF_SF_RESIDENT=1: one CTA per SM with a small shared-memory footprint, dealt (tile, split) items round-robin,
+    // so that the linear block (HBM) and the int8 GEMM (tensor cores, L2) share every SM when they run on two streams
+    static const bool resident = getenv("BTF_SF_RESIDENT") != nullptr && getenv("BTF_SF_RESIDENT")[0] != '0';
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+    // split-K partials are summed in split order by the recombination kernel
+    int nsplit = 1;
+    const int target = resident ? 8 * sms : 2 * sms;          // resident: 8 items per CTA; classic: one wave of two CTAs per SM
+    if (m_tiles < target) {
+        nsplit = target / m_tiles;       // never a partial last wave
+        if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
+        if (nsplit > (trans ? 1 : w.nsplit_b_row)) nsplit = trans ? 1 : w.nsplit_b_row;
+    }
+    { const int cps = (nchunks + nsplit - 1) / nsplit; nsplit = (nchunks + cps - 1) / cps; }
+    if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
+    else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
+    else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
+    return nsplit;
+}
+
+// 4. recombination of the int32 planes (skipped when the fused epilogue already wrote them) and the sum of the
+//    linear-block partials: out[m][0..L) from D, out[m][L..L+K) from bpart[split][bpart_m0 + m][.] (row pitch of a
+//    split = bpart_rows)
+void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, bool product_done, int nsplit_b,
+                      long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st) {
+    const int L = K * (K + 1) / 2;
+    const int ncy = (L + 31) / 32;
+    if (product_done)
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D, m_pad, w.expo, w.bpart, nsplit_b, m_valid, L, K, out, ncy,
+                                                                       bpart_m0, bpart_rows);
+    else
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D, m_pad, w.expo, w.bpart, nsplit_b, m_valid, L, K, out, 0,
+                                                                             bpart_m0, bpart_rows);
+}
+
+// All four stages on one stream.
 // trans = false: m = local row, contraction over p (B = cnt [nloc][ldb = Ppad], F = V [P][K], S [nloc_pad][lds])
 // trans = true : m = p, contraction over local rows (B = cntT [P][ldb = nloc_pad], F = W local [nloc][K], S the same array)
 int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
                     long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,
                     cudaStream_t st) {
-    const int L = K * (K + 1) / 2;
-    const long long ldk = kdim_pad, ldn = m_pad;
-    // 1. column scales and digit planes of Z
-    cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
-    zmax_kernel<<<(f_rows + 127) / 128, 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
-    {
-        const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
-        static size_t zs_set = 0;
-        if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
-        zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, ldk);
-    }
-    // 2. exact product block on the tensor cores: fused (counts on the M side, recombination in the epilogue) when
-    //    its tiles fill the GPU, else through the int32 intermediate with split-K
+    stats_i8_digits(w, K, F, f_rows, kdim_pad, st);
     if (w.ev[0]) cudaEventRecord(w.ev[0], st);
-    const bool no_fused = getenv("BTF_STATS_I8_NOFUSED") != nullptr, force_fused = getenv("BTF_STATS_I8_FUSED") != nullptr;
-    // (measured on C2: the fused epilogue's FP64 stores are not hidden under the next tile, 0.29 + 0.50 ms against
-    //  0.27 + 0.35 ms + 0.08 ms of recombination, so the int32 route is the default and the fused one is opt-in)
-    int fused = (no_fused || !force_fused) ? 1 : launch_i8gemm_fused(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, ldk, L,
-                                                                     kdim_pad, w.expo, out, L + K, 0, st);
-    if (fused > 1) return 1;
-    if (fused == 1 &&
-        launch_i8gemm(w.planes, ldk, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, ldn, st))
-        return 1;
+    const int pr = stats_i8_product(w, K, B, ldb, kdim_pad, m_valid, m_pad, out, st);
+    if (pr != 0 && pr != 10) return 1;
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
-    // 3. linear block in FP64
-    const int nchunks = kdim_pad / 32;
-    const int m_tiles = (m_valid + 127) / 128;
-    // enough CTAs for two per SM; split-K partials are summed in split order by the recombination kernel
-    int nsplit = 1;
-    if (m_tiles < 296) {
-        nsplit = 296 / m_tiles;          // one full wave of two CTAs per SM, never a partial second wave
-        if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
-        if (nsplit > (trans ? 1 : w.nsplit_b_row)) nsplit = trans ? 1 : w.nsplit_b_row;
-    }
-    { const int cps = (nchunks + nsplit - 1) / nsplit; nsplit = (nchunks + cps - 1) / cps; }
-    if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
-    else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
-    else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, w.bpart, st); }
+    const int nsplit = stats_i8_linear(w, trans, K, S, lds, F, kdim_pad, m_valid, st);
     if (w.ev[2]) cudaEventRecord(w.ev[2], st);
-    // 4. recombination of the int32 planes (not on the fused path) and the sum of the linear-block partials
-    const int ncy = (L + 31) / 32;
-    if (fused == 0)
-        i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out, ncy);
-    else
-        i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D, ldn, w.expo, w.bpart, nsplit, m_valid, L, K, out, 0);
+    stats_i8_combine(w, K, m_valid, m_pad, pr == 10, nsplit, 0, m_valid, out, st);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

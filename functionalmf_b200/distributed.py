@@ -66,3 +66,35 @@ def agree_unique_id():
     from .engine import nccl_unique_id
     uid = nccl_unique_id() if dist.get_rank() == 0 else None
     return broadcast_bytes(uid, 0)
+
+
+def agree_seed(seed, src=0):
+    """Every rank returns rank ``src``'s seed (the replicated hyper-parameter steps need one Philox key)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError('a sharded model needs torch.distributed to be initialised (it agrees on the RNG seed '
+                           'and the NCCL unique id)')
+    return int.from_bytes(broadcast_bytes(int(seed).to_bytes(8, 'little'), src), 'little')
+
+
+def state_digest(arrays):
+    """Order-sensitive checksum of a list of float arrays (bit patterns, so NaN-safe)."""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def assert_same_on_all_ranks(arrays, what='state'):
+    """Raise on every rank if the arrays differ between ranks."""
+    import torch.distributed as dist
+    mine = state_digest(arrays)
+    box = [None] * dist.get_world_size()
+    dist.all_gather_object(box, mine)
+    if len(set(box)) != 1:
+        raise ValueError('sharded model: %s differs between ranks (digests %s); pass identical *_init / *_true arrays '
+                         'and seed on every rank' % (what, [b[:8] for b in box]))

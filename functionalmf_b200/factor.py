@@ -49,7 +49,11 @@ class _BayesianModel(object):
         nsteps = nburn + nthin * nsamples
         if callback is not None:
             return self._run_gibbs_callback(data, nburn, nthin, nsamples, verbose, print_freq, callback, **kwargs)
-        self._begin(data)
+        self._full_check = True          # one whole-buffer checksum per chain
+        try:
+            self._begin(data)
+        finally:
+            self._full_check = False
         if track_mu:
             self._engine.track_mu_stats(True)
         for ev in getattr(self, '_evaluators', {}).values():
@@ -93,6 +97,8 @@ class _BayesianModel(object):
                 print('\tStep {}'.format(step))
             self.resample(data, **kwargs)
             callback(self, data, step, **kwargs)
+            if getattr(self, '_data_nbytes', 0) > self.full_checksum_bytes:
+                self.invalidate_data()       # a callback may edit a large array in place: never trust the sample
             if step >= nburn and (step - nburn) % nthin == 0:
                 sidx = (step - nburn) // nthin
                 inferred = self.inferred_variables()
@@ -138,6 +144,12 @@ class BayesianTensorFiltering(_BayesianModel):
         seed = eng_kw.pop('seed', None)
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 % (2 ** 63)
+        sharded = self._shard is not None and self._shard.world_size > 1
+        if sharded:
+            # sigma2, nu2, lam2 and the Tau2 chain are replicated, not communicated: every rank must run the same
+            # Philox key.  Rank 0's seed wins (a per-process np.random draw would differ from rank to rank).
+            from .distributed import agree_seed
+            seed = agree_seed(int(seed))
         opts = dict(sigma2_a=sigma2_a, sigma2_b=sigma2_b, stability=stability,
                     force_psd=int(bool(force_psd)), force_psd_eps=force_psd_eps,
                     force_psd_attempts=int(force_psd_attempts), seed=int(seed),
@@ -202,6 +214,13 @@ class BayesianTensorFiltering(_BayesianModel):
             eng.init_state(L.INIT_V)              # prior MVN draw per column (factor.py:235-242)
         self._after_base_init()
         self._pull_state()
+        if sharded:
+            # user-supplied *_init / *_true arrays must agree too: the sweep exchanges only the owned blocks
+            from .distributed import assert_same_on_all_ranks
+            assert_same_on_all_ranks(
+                [self.W, self.V, self.Tau2, self.Tau2_a, self.Tau2_b, self.Tau2_c] +
+                [np.asarray([float(np.ravel(getattr(self, n))[0]) for n in self._scalar_names()])],
+                what='initial state (W, V, Tau2 chain, scalars)')
 
     # ---- hooks for subclasses
     def _likelihood_options(self):
@@ -251,13 +270,31 @@ class BayesianTensorFiltering(_BayesianModel):
             return arr[r0:r1]
         return arr
 
-    @staticmethod
-    def _fingerprint(arr):
+    # ---- device copy of the data: re-uploaded whenever the array the caller passes has changed.
+    # The reference reads ``data`` afresh on every call (factor.py:306-311); the engine keeps the compact
+    # pre-reduction of it in HBM, so "has it changed" is decided by a checksum over the WHOLE buffer
+    # (sum and xor of the 64-bit patterns: any single-element edit changes it), not by sampling:
+    #   * run_gibbs: always the full checksum, once per chain;
+    #   * resample(): the full checksum for arrays up to ``full_checksum_bytes`` (256 MB, ~30 ms); above that one
+    #     checksum pass per sweep would cost more than the sweep itself, so a 2^20-element strided sample is used
+    #     and in-place edits of larger arrays must be announced with ``model.invalidate_data()``.
+    full_checksum_bytes = 256 << 20
+
+    def invalidate_data(self):
+        """Forget the device copy of the data: the next resample / run_gibbs uploads it again."""
+        self._data_key = None
+
+    @classmethod
+    def _fingerprint(cls, arr, full=False):
         a = np.asarray(arr)
-        flat = a.reshape(-1)
-        step = max(1, flat.size // 4096)
-        sample = np.nan_to_num(flat[::step][:4096].astype(np.float64), nan=-1.2345)
-        return (id(arr), a.shape, float(sample.sum()), float((sample * np.arange(1, sample.size + 1)).sum()))
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        bits = a.reshape(-1).view(np.uint64)
+        if not full and a.nbytes > cls.full_checksum_bytes:
+            bits = bits[::max(1, bits.size >> 20)]
+        with np.errstate(over='ignore'):
+            return (a.shape, int(bits.size), int(np.add.reduce(bits, dtype=np.uint64)),
+                    int(np.bitwise_xor.reduce(bits)) if bits.size else 0)
 
     def _begin(self, data):
         self._upload(data)
@@ -369,7 +406,8 @@ class GaussianBayesianTensorFiltering(BayesianTensorFiltering):
     def _upload(self, data):
         Y = np.asarray(data)
         assert len(Y.shape) == 3 or len(Y.shape) == 4, 'Observations must be 3- or 4-tensor.'
-        key = self._fingerprint(data)
+        key = self._fingerprint(data, getattr(self, '_full_check', False))
+        self._data_nbytes = int(np.asarray(data).nbytes)
         if key != self._data_key:
             self._engine.set_data_gaussian(self._local_rows(Y))
             self._data_key = key
@@ -411,11 +449,24 @@ class BinomialBayesianTensorFiltering(GaussianBayesianTensorFiltering):
 
     @nu2.setter
     def nu2(self, value):
-        pass   # the per-cell variances live on the device (omega = 1/nu2)
+        # the per-cell variances live on the device as omega = 1 / nu2 (redrawn at the start of every resample,
+        # factor.py:447-460, so like in the reference an assignment only lasts until the next sweep)
+        v = np.asarray(value, dtype=np.float64)
+        shape = (self._engine.nloc, self.ncols, self.ndepth)
+        if v.shape != shape:
+            raise ValueError('nu2 of a Polya-Gamma model is the per-cell tensor 1/omega of shape %r, got %r'
+                             % (shape, v.shape))
+        with np.errstate(divide='ignore'):
+            self._engine.set('omega', np.where(np.isfinite(v) & (v > 0), 1.0 / v, 0.0))
+
+    def _init_nu2(self):
+        pass   # factor.py:433: the PG models start from nu2 = 0 and redraw it at the top of every resample
 
     def _upload(self, data):
         Y, N = data
-        key = (self._fingerprint(Y), self._fingerprint(N))
+        full = getattr(self, '_full_check', False)
+        key = (self._fingerprint(Y, full), self._fingerprint(N, full))
+        self._data_nbytes = int(np.asarray(Y).nbytes)
         if key != self._data_key:
             self._engine.set_data_binomial(self._local_rows(np.asarray(Y)), self._local_rows(np.asarray(N)))
             self._data_key = key
@@ -493,7 +544,8 @@ class NegativeBinomialBayesianTensorFiltering(BinomialBayesianTensorFiltering):
 
     def _upload(self, data):
         Y = np.asarray(data)
-        key = self._fingerprint(data)
+        key = self._fingerprint(data, getattr(self, '_full_check', False))
+        self._data_nbytes = int(np.asarray(data).nbytes)
         if key != self._data_key:
             self._engine.set_data_negbin(self._local_rows(Y))
             self._data_key = key

@@ -167,12 +167,14 @@ def row_stats(V, cw, sw):
     return A, b
 
 
-def step_W(W, V, cw, sw, sigma2, z):
+def step_W(W, V, cw, sw, sigma2, z, row_index=None):
     """GaussianBTF._resample_W (factor.py:313-362) with explicit noise z [N, K].
 
     Returns (W_new, diag) where diag holds per-row Q (with the I/sigma2 prior,
     zero outside the leading d x d block), its lower Cholesky factor and the
-    conditional mean.
+    conditional mean.  ``row_index`` (optional) gives the position of every
+    passed row in the full W (a sample of rows of a large problem): the first K
+    rows are lower triangular, d = min(i + 1, K) with i the GLOBAL row index.
     """
     N, K = W.shape
     A, b = row_stats(V, cw, sw)
@@ -181,7 +183,7 @@ def step_W(W, V, cw, sw, sigma2, z):
     Ls = np.zeros((N, K, K))
     means = np.zeros((N, K))
     for i in range(N):
-        d = min(i + 1, K)
+        d = min((i if row_index is None else int(row_index[i])) + 1, K)
         Q = A[i, :d, :d] + np.eye(d) / sigma2
         L = np.linalg.cholesky(Q)
         mean = sla.cho_solve((L, True), b[i, :d])

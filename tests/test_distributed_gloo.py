@@ -64,3 +64,34 @@ def test_two_rank_plumbing(tmp_path):
     partial = rs.normal(size=(2, 37, 4))
     assert np.array_equal(a[132:132 + 3000], W.ravel()) and np.array_equal(b[132:132 + 3000], W.ravel())
     assert np.allclose(a[132 + 3000:], partial.sum(0).ravel()) and np.allclose(a[132 + 3000:], b[132 + 3000:])
+
+
+def _seed_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from functionalmf_b200.distributed import agree_seed, assert_same_on_all_ranks
+    # every rank draws its own seed (what the constructor does without seed=): rank 0's must win everywhere
+    mine = 1000 + 17 * rank
+    got = agree_seed(mine)
+    same = np.arange(6.0).reshape(2, 3)
+    assert_same_on_all_ranks([same, np.array([np.nan, 1.0])], what='identical arrays')
+    raised = False
+    try:
+        assert_same_on_all_ranks([same + (1e-300 if rank == 1 else 0.0)], what='arrays that differ in one bit')
+    except ValueError:
+        raised = True
+    np.save(os.path.join(out_dir, 's%d.npy' % rank), np.array([got, float(raised)]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_seed_agreement_and_state_check(tmp_path):
+    """sharded models replicate sigma2 / nu2 / lam2 / Tau2, so the Philox seed and the initial
+    state must be identical on every rank; the constructor enforces it with these two helpers."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_seed_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = np.load(tmp_path / 's0.npy')
+    b = np.load(tmp_path / 's1.npy')
+    assert a[0] == 1000 and b[0] == 1000          # rank 0's seed on both ranks
+    assert a[1] == 1.0 and b[1] == 1.0            # the mismatch is reported on every rank

@@ -18,7 +18,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
-    for (N, M, T, R, K, order) in [(1024, 64, 32, 3, 16, 2), (700, 37, 12, 2, 5, 1), (512, 16, 10, 1, 32, 2)]:
+    for (N, M, T, R, K, order) in [(1024, 64, 32, 3, 16, 2), (700, 37, 12, 2, 5, 1), (512, 16, 10, 1, 32, 2), (900, 19, 24, 3, 8, 3)]:
         rs = np.random.RandomState(7)
         W = rs.normal(size=(N, K)); W[np.triu_indices(K, k=1)] = 0
         V = rs.normal(size=(M, T, K)).cumsum(axis=1) * 0.3
@@ -78,10 +78,35 @@ def main():
             print('shape %s world %d: max normwise diff vs single GPU %.3e %s | ms/sweep sharded %.3f single %.3f'
                   % ((N, M, T, R, K, order), world, worst, 'OK' if good else 'MISMATCH', ms / 5, ms1 / 5), flush=True)
         dist.barrier()
+    ok = model_level_check(rank, world, local) and ok
     dist.destroy_process_group()
     if rank == 0:
         print('MULTI_GPU_CHECK', 'PASS' if ok else 'FAIL', flush=True)
         sys.exit(0 if ok else 1)
+
+
+def model_level_check(rank, world, local):
+    """a sharded model built WITHOUT seed= (every process draws its own from np.random) must still
+    run one chain: the constructor agrees on rank 0's seed, so sigma2 / lam2 / nu2 / Tau2 / W / V are bit-identical on
+    every rank after a few sweeps, and run_gibbs returns the same samples everywhere."""
+    from functionalmf_b200 import GaussianBayesianTensorFiltering
+    N, M, T, R, K = 640, 24, 16, 2, 8
+    rs = np.random.RandomState(3)
+    Y = rs.normal(size=(N, M, T, R))
+    Y[rs.random_sample(Y.shape) < 0.2] = np.nan
+    np.random.seed(1000 + rank)                      # different per-process numpy streams
+    sh = Shard(rank, world, N, M)
+    model = GaussianBayesianTensorFiltering(N, M, T, nembeds=K, tf_order=1, shard=sh, device=local)
+    r0, r1 = sh.rows
+    res = model.run_gibbs(Y[r0:r1], nburn=2, nthin=1, nsamples=3, verbose=False)
+    from functionalmf_b200.distributed import state_digest
+    digest = state_digest([res['W'], res['V'], res['Tau2'], res['sigma2'], res['lam2'], model.Tau2_a, model.nu2 * np.ones(1)])
+    box = [None] * world
+    dist.all_gather_object(box, digest)
+    good = len(set(box)) == 1 and np.all(np.isfinite(res['V']))
+    if rank == 0:
+        print('model-level (no seed=) world %d: %s' % (world, 'identical on all ranks OK' if good else 'RANKS DIFFER'), flush=True)
+    return good
 
 
 if __name__ == '__main__':
