@@ -34,10 +34,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of i8gemm_kernel (mean of the row and the column launch)
-# from the ncu --set full capture of the same command (profiles/); None until captured
-I8_TRAFFIC = {('c2', 1): 4.325e8}     # profiles/r1_ncu_i8_summary.txt: rows 0.340 + 0.005 GB, columns 0.273 + 0.247 GB
-
 WORKLOADS = {
     # name: N, M, T, R, K, order, nan_frac
     'c2': dict(N=4096, M=1024, T=64, R=3, K=16, order=2, nan=0.2,
@@ -221,6 +217,107 @@ def cpu_baseline(cfg, budget_s=20.0, seed=2):
             'sweep_seconds_est': sweep_s, 'prereduce_seconds_sample': t_pre}
 
 
+# ----------------------------------------------------------------------------- CPU baseline (the unmodified reference)
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, 'functionalmf', 'factor.py'))
+
+
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (installed there by __graft_entry__.build() with
+    `pip install --no-deps --target baseline/_ref /root/reference`; git-ignored, travels with gpurun) under the three
+    import shims of oracle/shims: scikit-sparse (CHOLMOD -> banded LAPACK Cholesky), pypolyagamma, SharedArray are not
+    installable offline.  Only this arm may execute anything under oracle/."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    for pth in (os.path.join(ROOT, 'oracle', 'shims'), REF_DIR):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import functionalmf.factor as F
+    assert os.path.abspath(F.__file__).startswith(REF_DIR), F.__file__
+    return F
+
+
+class ReferenceSample(object):
+    """The reference's own sampler steps on a bounded sample of the workload:
+    GaussianBayesianTensorFiltering._resample_W (factor.py:313-362) on `nr` rows at full M, T;
+    _resample_V (factor.py:364-409) on `nc` columns at full N, T; _resample_nu2 on the row sample; sigma2 / Tau2 / lam2
+    on the full column count.  Per-row and per-column costs do not depend on the other dimension's count (Python
+    loops over rows / columns), so one sweep of the full tensor costs
+        t_hyper + (t_nu2 + t_W) N / nr + t_V M / nc.
+    Small workloads (C1) run model.resample(Y) on the whole tensor instead."""
+
+    def __init__(self, cfg, nr=16, nc=1, seed=2):
+        F = import_reference()
+        self.cfg = cfg
+        N, M, T, R, K, order = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K'], cfg['order']
+        self.full = N * M * T <= 2_000_000
+        W, V = truth(cfg, seed)
+        np.random.seed(seed)
+        kw = dict(nembeds=K, tf_order=order, sigma2_init=0.5, lam2_init=0.1, nu2_init=1.0)
+        if self.full:
+            self.nr, self.nc = N, M
+            self.Y = np.empty((N, M, T, R))
+            fill_rows(self.Y, W, V, 0, N, cfg, seed)
+            self.model = F.GaussianBayesianTensorFiltering(N, M, T, **kw)
+            return
+        self.nr, self.nc = max(K, min(N, nr)), max(1, min(M, nc))        # factor.py:233 needs nrows >= nembeds
+        self.Yr = np.empty((self.nr, M, T, R))
+        fill_rows(self.Yr, W[:self.nr], V, 0, self.nr, cfg, seed)
+        self.Yc = np.empty((N, self.nc, T, R))
+        for a in range(0, N, 512):
+            fill_rows(self.Yc, W, V[:self.nc], a, min(N, a + 512), cfg, seed + 1)
+        self.rows = F.GaussianBayesianTensorFiltering(self.nr, M, T, **kw)
+        self.cols = F.GaussianBayesianTensorFiltering(N, self.nc, T, **kw)
+
+    def step(self):
+        """One sampled sweep; returns (wall seconds of the sample, estimated seconds of the full sweep)."""
+        N, M = self.cfg['N'], self.cfg['M']
+        t0 = time.perf_counter()
+        if self.full:
+            self.model.resample(self.Y)
+            dt = time.perf_counter() - t0
+            return dt, dt
+        m = self.rows
+        m._resample_nu2(self.Yr)
+        t1 = time.perf_counter()
+        m._resample_sigma2(); m._resample_Tau2(); m._resample_lam2()
+        t2 = time.perf_counter()
+        m._resample_W(self.Yr)
+        t3 = time.perf_counter()
+        self.cols._resample_V(self.Yc)
+        t4 = time.perf_counter()
+        est = (t2 - t1) + ((t1 - t0) + (t3 - t2)) * (N / float(self.nr)) + (t4 - t3) * (M / float(self.nc))
+        return t4 - t0, est
+
+    def describe(self, reps):
+        if self.full:
+            return ('unmodified reference (baseline/_ref, functionalmf.factor.GaussianBayesianTensorFiltering.resample) on the '
+                    'whole tensor, %d sweeps; shims: CHOLMOD -> banded LAPACK Cholesky' % reps)
+        return ('unmodified reference (baseline/_ref): _resample_W on %d of %d rows and _resample_nu2 on the same rows at full '
+                'M,T; _resample_V on %d of %d columns at full N,T; sigma2/Tau2/lam2 on all %d columns; %d repetitions; '
+                'sweep = t_hyper + (t_nu2 + t_W) N/nr + t_V M/nc (extrapolated); single Python thread like the reference '
+                '(nthreads is ignored, factor.py:36-37); shims: CHOLMOD -> banded LAPACK Cholesky'
+                % (self.nr, self.cfg['N'], self.nc, self.cfg['M'], self.cfg['M'], reps))
+
+
+def cpu_baseline_reference(cfg, budget_s=20.0, seed=2):
+    """cpu_baseline for our arm: a few sampled sweeps of the unmodified reference within `budget_s` seconds."""
+    smp = ReferenceSample(cfg, seed=seed)
+    reps, est_sum, t_start = 0, 0.0, time.perf_counter()
+    while True:
+        _, est = smp.step()
+        est_sum += est
+        reps += 1
+        if time.perf_counter() - t_start > budget_s or reps >= 200:
+            break
+    sweep_s = est_sum / reps
+    return {'value': 1.0 / sweep_s, 'unit': 'sweeps/s', 'cores': 1, 'kind': 'reference', 'sample': smp.describe(reps),
+            'sweep_seconds_est': sweep_s, 'host_cores_available': os.cpu_count()}
+
+
 def bind_to_gpu_numa_node(device):
     """Best effort: run this process on the CPUs local to the GPU's PCIe root so that the pinned
     host buffers (first-touch) live on the near NUMA node -- the H2D copy of Y runs at ~51 GB/s
@@ -248,11 +345,117 @@ def bind_to_gpu_numa_node(device):
     return None
 
 
+# ----------------------------------------------------------------------------- roofline
+def _measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def _ncu_traffic(kernel_key, workload, world):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed ncu
+    --set full capture of this command (profiles/r2_traffic.json, written by tools/ncu_summary.py), else None."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+        return tab.get('%s/g%d' % (workload, world), {}).get(kernel_key)
+    except Exception:
+        return None
+
+
+def build_roofline(args, cfg, eng, phases, ms_step, world, device):
+    """`roofline` = the kernel family with the largest time share in THIS run (serialised per-phase CUDA-event times),
+    plus the whole sweep against the HBM and FP64 bounds of BASELINE.md section 4, plus the other large families."""
+    from functionalmf_b200.engine import fp64_peak, i8_peak
+    N, M, T, R, K, order = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K'], cfg['order']
+    cells = float(N) * M * T
+    Lp = K * (K + 1) // 2
+    n, kd = T * K, (order + 1) * K
+    pk = _measured_peaks()
+    hbm_peak = pk.get('hbm_gbs') or 6650.0
+    hbm_src = 'MEASURED_PEAKS.json hbm_gbs' if pk.get('hbm_gbs') else 'fallback (B200_PROFILING.md)'
+    dmma = fp64_peak(device, 1, 20000)
+    dfma = fp64_peak(device, 0, 20000)
+    fp64 = max(dmma, dfma)
+    i8pk = i8_peak(device, 4000)
+    gemm_ms = phases.get('row_i8gemm', 0.0) + phases.get('col_i8gemm', 0.0)
+    lin_ms = phases.get('row_linear', 0.0) + phases.get('col_linear', 0.0)
+    band_ms = phases.get('band_solve', 0.0)
+    stats_ms = phases['row_stats'] + phases['col_stats']
+    fam = {}
+    # linear block (sf_kernel): reads S once per contraction, 8 B per cell
+    if lin_ms > 0:
+        byt = 2.0 * cells * 8.0 / world
+        fam['sf_kernel'] = {'bound': 'hbm', 'achieved': byt / (lin_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                            'kernel': 'sf_kernel (FP64 linear block of the row and column statistics, 2 launches per sweep)',
+                            'ms_per_sweep': lin_ms, 'algorithmic_bytes_per_sweep_per_gpu': byt,
+                            'algorithmic_bytes_per_launch': byt / 2.0, 'peak_source': hbm_src,
+                            'traffic': _ncu_traffic('sf_kernel', args.workload, world)}
+    # product block (i8gemm_kernel): executed int8 operations and the FP64 flops they replace
+    if gemm_ms > 0:
+        nloc, nloc_pad = eng.nloc, -(-eng.nloc // 128) * 128
+        nall_pad = -(-N // 128) * 128 if world > 1 else nloc_pad
+        P, Ppad = M * T, -(-(M * T) // 256) * 256
+        ploc = eng.Mloc * T
+        ops = 2.0 * (8 * Lp) * (float(nloc) * Ppad + float(ploc) * nall_pad)
+        alg = 4.0 * cells * Lp / world
+        fam['i8gemm_kernel'] = {'bound': 'tensor', 'achieved': ops / (gemm_ms * 1e-3) / 1e12, 'peak': i8pk, 'unit': 'TFLOP/s',
+                                'kernel': 'i8gemm_kernel (tcgen05.mma.kind::i8, exact digit-plane contraction of the product block, '
+                                          '2 launches per sweep; achieved = int8 operations AS EXECUTED: 8 digit planes are an '
+                                          'implementation choice, the algorithmic FP64 work is listed beside it)',
+                                'ms_per_sweep': gemm_ms, 'executed_int8_ops_per_sweep_per_gpu': ops,
+                                'algorithmic_fp64_flops_per_sweep_per_gpu': alg,
+                                'algorithmic_fp64_tflops_at_this_time': alg / (gemm_ms * 1e-3) / 1e12, 'fp64_dmma_peak': dmma,
+                                'peak_source': 'btf_i8_peak in this run (resident-operand tcgen05 loop on every SM, %.0f Top/s); '
+                                               'MEASURED_PEAKS.json has no int8 entry (2 x its bf16 burst = %.0f)'
+                                               % (i8pk, 2.0 * (pk.get('bf16_tflops') or 1634.5)),
+                                'traffic': _ncu_traffic('i8gemm_kernel', args.workload, world)}
+    # band solve (band_lookahead_kernel): one launch, latency bound; factor traffic + FP64 flops
+    if band_ms > 0:
+        mloc = eng.Mloc
+        byt = 3.0 * n * (kd + 1) * 8.0 * mloc + float(mloc) * T * (Lp + K) * 8.0
+        flop = float(mloc) * n * kd * kd
+        fam['band_lookahead_kernel'] = {'bound': 'hbm', 'achieved': byt / (band_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                        'kernel': 'band_lookahead_kernel (block-banded Cholesky + MVN draw per column; latency bound)',
+                                        'ms_per_sweep': band_ms, 'algorithmic_bytes_per_launch': byt,
+                                        'algorithmic_flops_per_launch': flop,
+                                        'fp64_tflops': flop / (band_ms * 1e-3) / 1e12, 'fp64_peak': fp64,
+                                        'fp64_frac': flop / (band_ms * 1e-3) / 1e12 / fp64 if fp64 > 0 else None,
+                                        'peak_source': hbm_src, 'traffic': _ncu_traffic('band_lookahead_kernel', args.workload, world)}
+    if not fam:
+        # FP64 DMMA statistics path (BTF_STATS_NO_I8, PG models, small tensors)
+        flop = 4.0 * cells * (Lp + K) / world
+        fam['stats_kernel'] = {'bound': 'tensor', 'achieved': flop / (stats_ms * 1e-3) / 1e12 if stats_ms > 0 else 0.0, 'peak': fp64,
+                               'unit': 'TFLOP/s', 'kernel': 'stats_kernel (FP64 DMMA sufficient statistics, 2 launches per sweep)',
+                               'ms_per_sweep': stats_ms, 'algorithmic_flops_per_sweep_per_gpu': flop,
+                               'peak_source': 'btf_fp64_peak in this run (DMMA %.2f, DFMA %.2f TFLOP/s)' % (dmma, dfma),
+                               'traffic': _ncu_traffic('stats_kernel', args.workload, world)}
+    for v in fam.values():
+        v['frac'] = v['achieved'] / v['peak'] if v['peak'] else None
+    top = max(fam, key=lambda k: fam[k]['ms_per_sweep'])
+    roof = dict(fam[top])
+    roof['dominant_by'] = 'largest serialised time share of the sweep in this run (%s: %.3f ms of %.3f ms phase total)' % (
+        top, fam[top]['ms_per_sweep'], sum(v for k, v in phases.items() if k in
+                                           ('nu2_or_pg', 'sigma2', 'tau2', 'lam2', 'row_stats', 'row_solve', 'col_stats', 'band_solve', 'comm')))
+    roof['other_kernels'] = {k: v for k, v in fam.items() if k != top}
+    # the whole sweep against BASELINE.md section 4
+    B_alg = 2.0 * cells * 9.0 / world
+    F_alg = (4.0 * cells * (Lp + K) + float(M) * n * kd * kd + float(N) * K ** 3 / 3.0) / world
+    t = ms_step * 1e-3
+    roof['sweep'] = {'ms_per_step': ms_step, 'B_alg_bytes_per_gpu': B_alg, 'F_alg_flops_per_gpu': F_alg,
+                     'hbm_achieved_gbs': B_alg / t / 1e9, 'hbm_peak_gbs': hbm_peak, 'hbm_frac': B_alg / t / 1e9 / hbm_peak,
+                     'fp64_equiv_tflops': F_alg / t / 1e12, 'fp64_peak_tflops': fp64,
+                     'fp64_frac': F_alg / t / 1e12 / fp64 if fp64 > 0 else None,
+                     'note': 'B_alg = 2 x cells x 9 B, F_alg = 4 cells (L+K) + M n kd^2 + N K^3/3 (BASELINE.md section 4); '
+                             'fp64_frac > 1 is possible because the product block runs on the int8 tensor cores'}
+    return roof
+
+
 # ----------------------------------------------------------------------------- our arm
 def bench_ours(args):
     import torch
     import torch.distributed as dist
-    from functionalmf_b200.engine import Engine, fp64_peak, hbm_copy_gbs, pinned_empty
+    from functionalmf_b200.engine import Engine, pinned_empty
     from functionalmf_b200.distributed import Shard, agree_unique_id
 
     cfg = dict(WORKLOADS[args.workload])
@@ -354,94 +557,32 @@ def bench_ours(args):
 
     out = None
     if rank == 0:
-        cells = float(N) * M * T
-        Lp = K * (K + 1) // 2
-        stats_ms = phases['row_stats'] + phases['col_stats']
-        flops_stats = 4.0 * cells * (Lp + K) / world        # per rank: both contractions, 2 flop per FMA
-        dmma = fp64_peak(local, 1, 20000)
-        dfma = fp64_peak(local, 0, 20000)
-        peak = max(dmma, dfma)
-        achieved = flops_stats / (stats_ms * 1e-3) / 1e12 if stats_ms > 0 else 0.0
-        peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        hbm_peak = None
-        if os.path.exists(peaks_file):
-            try:
-                hbm_peak = json.load(open(peaks_file)).get('hbm_gbs')
-            except Exception:
-                hbm_peak = None
-        hbm_src = 'MEASURED_PEAKS.json' if hbm_peak else 'fallback (B200_PROFILING.md)'
-        hbm_peak = hbm_peak or 6650.0
-        bytes_stats = 2.0 * cells * 9.0 / world
-        # DRAM traffic per launch of the dominant kernel from the ncu --set full capture of this
-        # workload (profiles/r1_ncu_stats_zpre_summary.txt: rows 2.504 GB read + 0.029 GB written,
-        # columns 2.436 GB + 0.144 GB); algorithmic bytes per launch are cells * 9 B = 2.416 GB
-        traffic = 2.5566e9 if (args.workload == 'c2' and world == 1) else None
-        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak if peak > 0 else None, 'traffic': traffic,
-                    'kernel': 'stats_kernel (row + column sufficient-statistic contractions, FP64 DMMA)',
-                    'flops_per_sweep_per_gpu': flops_stats, 'kernel_ms_per_sweep': stats_ms,
-                    'peak_source': 'btf_fp64_peak micro-benchmark in this run (DMMA %.2f, DFMA %.2f TFLOP/s); '
-                                   'MEASURED_PEAKS.json has no FP64 entry' % (dmma, dfma),
-                    'hbm': {'achieved': bytes_stats / (stats_ms * 1e-3) / 1e9 if stats_ms > 0 else None,
-                            'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src,
-                            'bytes_per_sweep_per_gpu': bytes_stats}}
-        gemm_ms = phases.get('row_i8gemm', 0.0) + phases.get('col_i8gemm', 0.0)
-        if gemm_ms > 0:
-            # integer-tensor-core path (stats_i8.cu): the dominant kernel is i8gemm_kernel, two launches per
-            # sweep.  Executed work: 8 digit planes x L product columns against the counts,
-            # 2 * (8 L) * rows * (padded contraction length) int8 operations per launch.
-            nloc, nloc_pad = eng.nloc, -(-eng.nloc // 128) * 128
-            P, Ppad = M * T, -(-(M * T) // 256) * 256
-            ops = 2.0 * (8 * Lp) * (float(nloc) * Ppad + float(P) * nloc_pad)
-            bf16 = None
-            if os.path.exists(peaks_file):
-                try:
-                    bf16 = json.load(open(peaks_file)).get('bf16_tflops')
-                except Exception:
-                    bf16 = None
-            i8_peak = 2.0 * (bf16 or 1634.5)
-            ach = ops / (gemm_ms * 1e-3) / 1e12
-            lin_ms = phases.get('row_linear', 0.0) + phases.get('col_linear', 0.0)
-            roofline = {
-                'bound': 'tensor', 'achieved': ach, 'peak': i8_peak, 'unit': 'TFLOP/s', 'frac': ach / i8_peak,
-                'traffic': I8_TRAFFIC.get((args.workload, world)),
-                'kernel': 'i8gemm_kernel (tcgen05.mma.kind::i8: exact digit-plane contraction of the product block '
-                          'of the row and the column statistics; int8 operations counted as executed)',
-                'ops_per_sweep_per_gpu': ops, 'kernel_ms_per_sweep': gemm_ms,
-                'peak_source': '2 x the measured dense bf16 rate of MEASURED_PEAKS.json (%s TFLOP/s burst; the int8 '
-                               'tensor rate of this part is twice its bf16 rate); no int8 entry there' % (bf16 or 'fallback 1634.5'),
-                'algorithmic_fp64': {
-                    'flops_per_sweep_per_gpu': 4.0 * cells * Lp / world,
-                    'tflops_at_gemm_time': 4.0 * cells * Lp / world / (gemm_ms * 1e-3) / 1e12,
-                    'fp64_dmma_peak': dmma,
-                    'note': 'FP64 flops of the product block (SURVEY 8d) divided by the int8 GEMM time: what the exact '
-                            'fixed-point formulation delivers against the FP64 pipe it replaces'},
-                'linear_block': {'kernel': 'sf_kernel (FP64 DMMA, reads S once per contraction)',
-                                 'ms_per_sweep': lin_ms, 'bytes_per_sweep_per_gpu': 2.0 * cells * 8.0 / world,
-                                 'achieved_gbs': 2.0 * cells * 8.0 / world / (lin_ms * 1e-3) / 1e9 if lin_ms > 0 else None,
-                                 'peak_gbs': hbm_peak, 'peak_source': hbm_src},
-                'statistics_ms_per_sweep': stats_ms,
-            }
         out = {
             'metric': 'Gibbs sweeps/sec', 'value': args.steps / (ms * 1e-3), 'unit': 'sweeps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak' if cfg.get('weak') else 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': cfg['label'], 'shape': [N, M, T, R], 'nembeds': K, 'tf_order': order,
-                       'nan_frac': cfg['nan'], 'l2': 'inputs (%.2f GB compact) larger than L2' % (cells * 9 / 1e9),
-                       'parallelism': 'rows+cols sharded x%d' % world if world > 1 else 'single GPU',
-                       'sweep': 'nu2,sigma2,Tau2,lam2,W,V (ref_compat lam2)'},
+            'config': workload_config(cfg, world),
+            'parallelism': 'rows+cols sharded x%d' % world if world > 1 else 'single GPU',
             'e2e': e2e,
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': roofline,
+            'roofline': build_roofline(args, cfg, eng, phases, ms / args.steps, world, local),
             'phases_ms': phases,
+            'phases_note': 'per-phase times are measured with the sweep serialised on one stream; in the timed run the '
+                           'tensor-core product block, the HBM-bound linear block and the hyper-parameter steps overlap '
+                           '(sum of phases > ms_per_step)',
             'state': st_final,
             'e2e_gpu_launches': int(e2e_launches),
             'datagen_seconds': t_gen,
         }
         if world == 1 and not args.no_cpu_baseline and not device_data:
-            out['cpu_baseline'] = cpu_baseline(cfg, budget_s=args.cpu_budget)
+            if reference_available():
+                out['cpu_baseline'] = cpu_baseline_reference(cfg, budget_s=args.cpu_budget)
+                # second, stronger CPU baseline: the vectorised numpy/LAPACK restatement
+                out['cpu_baseline_port'] = cpu_baseline(cfg, budget_s=min(10.0, args.cpu_budget))
+            else:
+                out['cpu_baseline'] = cpu_baseline(cfg, budget_s=args.cpu_budget)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -449,27 +590,55 @@ def bench_ours(args):
 
 
 # ----------------------------------------------------------------------------- reference arm
+def workload_config(cfg, world):
+    """The `config` dict both arms print (identical, so the driver's same_config check holds)."""
+    N, M, T, R, K, order = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K'], cfg['order']
+    return {'workload': cfg['label'], 'shape': [N, M, T, R], 'nembeds': K, 'tf_order': order, 'nan_frac': cfg['nan'],
+            'l2': 'inputs (%.2f GB compact) larger than L2' % (float(N) * M * T * 9 / 1e9),
+            'sweep': 'nu2,sigma2,Tau2,lam2,W,V (ref_compat lam2)'}
+
+
 def bench_reference(args):
+    """--impl reference: the reference's own CPU implementation on the box's host cores.  Each step is one sampled
+    sweep (see ReferenceSample); `ms_per_step` is the wall time of that bounded sample, `value` the sweeps/s of the
+    FULL workload it implies (extrapolation stated in cpu_baseline.sample).  Without baseline/_ref the oracle port
+    is timed instead (kind 'port')."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
-    cfg = WORKLOADS[args.workload]
-    per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline(cfg, budget_s=per_step, seed=2 + i)
-        if i >= args.warmup:
-            vals.append(base['sweep_seconds_est'])
-    sweep_s = float(np.mean(vals))
-    N, M, T, R, K, order = cfg['N'], cfg['M'], cfg['T'], cfg['R'], cfg['K'], cfg['order']
-    base['value'] = 1.0 / sweep_s
+    cfg = dict(WORKLOADS[args.workload])
+    if cfg.get('weak'):
+        cfg['N'] = cfg['N'] * args.gpus
+    if not reference_available():
+        per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+        vals, wall, base = [], [], None
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            base = cpu_baseline(cfg, budget_s=per_step, seed=2 + i)
+            if i >= args.warmup:
+                vals.append(base['sweep_seconds_est']); wall.append(time.perf_counter() - t0)
+        sweep_s, step_s = float(np.mean(vals)), float(np.mean(wall))
+        base['value'] = 1.0 / sweep_s
+    else:
+        # size the sample so that warm-up + steps end within a few minutes
+        total = max(1, args.steps + args.warmup)
+        nc = 2 if total <= 12 else 1
+        nr = 32 if total <= 12 else 16
+        smp = ReferenceSample(cfg, nr=nr, nc=nc)
+        vals, wall = [], []
+        for i in range(total):
+            dt, est = smp.step()
+            if i >= args.warmup:
+                vals.append(est); wall.append(dt)
+        sweep_s, step_s = float(np.mean(vals)), float(np.mean(wall))
+        base = {'value': 1.0 / sweep_s, 'unit': 'sweeps/s', 'cores': 1, 'kind': 'reference',
+                'sample': smp.describe(args.steps), 'sweep_seconds_est': sweep_s, 'host_cores_available': os.cpu_count()}
     return {
         'impl': 'reference', 'metric': 'Gibbs sweeps/sec', 'value': 1.0 / sweep_s, 'unit': 'sweeps/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sweep_s * 1e3,
-        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': cfg['label'], 'shape': [N, M, T, R], 'nembeds': K, 'tf_order': order,
-                   'nan_frac': cfg['nan']},
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_s * 1e3,
+        'ms_per_full_sweep_est': sweep_s * 1e3, 'extrapolated': sweep_s != step_s,
+        'higher_is_better': True, 'scaling': 'weak' if cfg.get('weak') else 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(cfg, args.gpus),
         'cpu_baseline': base,
         'e2e': {'value': 1.0 / sweep_s, 'unit': 'sweeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,

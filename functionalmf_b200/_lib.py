@@ -94,6 +94,7 @@ SIGNATURES = {
     'btf_time_phases': (C.c_int, [_P, C.c_int32, _D, C.c_int32]),
     'btf_fp64_peak': (C.c_double, [C.c_int32, C.c_int32, C.c_int32]),
     'btf_hbm_copy_gbs': (C.c_double, [C.c_int32, C.c_size_t, C.c_int32]),
+    'btf_i8_peak': (C.c_double, [C.c_int32, C.c_int32]),
     'btf_pg_sample': (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, C.c_uint64]),
     'btf_rng_sample': (C.c_int, [C.c_int32, C.c_int32, C.c_double, _P, C.c_int64, C.c_uint64]),
     'btf_i8gemm_test': (C.c_double, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -467,3 +467,80 @@ extern "C" double btf_i8gemm_test(int device, const int8_t* A, const int8_t* B, 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return (double)ms;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Roofline denominator of the int8 tensor pipe: every SM issues tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32) on
+// operands that stay in shared memory - no loads, no epilogue - so the rate is the pipe's, not the memory system's.
+namespace btf {
+namespace {
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
+    extern __shared__ uint8_t smraw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* done = reinterpret_cast<uint64_t*>(sm + I8_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < I8_STAGE_BYTES / 4; e += 128) reinterpret_cast<uint32_t*>(sm)[e] = 0x01ff0201u * (uint32_t)(e % 7);
+    if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(I8_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t a0 = smem_u32(sm), b0 = a0 + I8_A_BYTES;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < I8_BK / 32; ++k)
+                umma_i8(tmem_d, umma_desc_sw128(a0 + 32 * k), umma_desc_sw128(b0 + 32 * k), (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(done);
+        mbar_wait(done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(tmem_d));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (v == 0x7fffffffu) sink[0] = (int)v;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I8_TMEM_COLS));
+}
+}  // namespace
+}  // namespace btf
+
+// int8 tensor throughput with resident operands, in Top/s (2 * MACs); best of 3 timed launches after a warm-up
+extern "C" double btf_i8_peak(int32_t device, int32_t iters) {
+    using namespace btf;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int smem = I8_STAGE_BYTES + 1024 + 64;
+    if (cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -2.0;
+    int* sink = nullptr;
+    if (cudaMalloc(&sink, 4) != cudaSuccess) return -2.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        i8_peak_kernel<<<sms, 128, smem>>>(iters, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -3.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = 2.0 * I8_BM * I8_BN * I8_BK * (double)iters * sms;
+        const double tops = ops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tops > best) best = tops;
+    }
+    if (cudaGetLastError() != cudaSuccess && best > 0) best = -4.0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}

@@ -251,6 +251,11 @@ def fp64_peak(device=0, mode=1, iters=20000):
     return L.load().btf_fp64_peak(int(device), int(mode), int(iters))
 
 
+def i8_peak(device=0, iters=4000):
+    """Measured int8 tensor-core rate (Top/s) with operands resident in shared memory."""
+    return L.load().btf_i8_peak(int(device), int(iters))
+
+
 def hbm_copy_gbs(device=0, nbytes=1 << 30, iters=5):
     return L.load().btf_hbm_copy_gbs(int(device), int(nbytes), int(iters))
 

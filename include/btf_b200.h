@@ -170,6 +170,9 @@ int  btf_time_phases(btf_engine* e, int32_t nsweeps, double* ms_out, int32_t nph
  * mode 0 = DFMA chains, 1 = mma.sync m8n8k4 f64 (DMMA).  Returns TFLOP/s. */
 double btf_fp64_peak(int32_t device, int32_t mode, int32_t iters);
 double btf_hbm_copy_gbs(int32_t device, size_t bytes, int32_t iters);
+/* int8 tensor-core throughput (tcgen05.mma.kind::i8, operands resident in shared memory, every SM busy):
+ * the measured denominator of the int8 GEMM's roofline.  Returns Top/s (2 x MAC). */
+double btf_i8_peak(int32_t device, int32_t iters);
 
 /* ---- sampler test hooks: out[e] ~ PG(b[e], z[e]) (replaces pypolyagamma pgdrawv, factor.py:459);
  * raw variates of the device generator: kind 0 normal, 1 gamma(param), 2 exponential, 3 uniform */
