@@ -62,6 +62,8 @@ struct btf_engine {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};   // forked inside a sweep: tensor-core product block | HBM-bound linear block
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk[2][16] = {{nullptr}};   // per column chunk of the V step: product block done | linear block done
+    int col_chunks = 4;          // BTF_COL_CHUNKS: the V step runs as a pipeline over this many column chunks
     bool overlap = true;         // BTF_NO_OVERLAP=1: everything on one stream (A/B runs)
     // state
     double *W = nullptr, *V = nullptr, *Tau2 = nullptr, *Tau2_a = nullptr, *Tau2_b = nullptr, *Tau2_c = nullptr;
@@ -88,6 +90,9 @@ struct btf_engine {
     // K1 on the integer tensor cores (stats_i8.cu): decided per data set, buffers allocated on first use
     bool i8_on = false, i8_decided = false;
     StatsI8Buffers i8{};
+    unsigned *cnt_rowsum = nullptr, *cnt_colsum = nullptr;   // sum of the counts of every local row / owned (j,t): guard of the fixed-point block
+    int *guard_n = nullptr, *guard_list = nullptr;           // [2] flagged counts (rows, columns), [nloc + Ploc] flagged indices
+    bool guard_on = true;        // BTF_I8_NO_GUARD=1 switches the element-wise guard off
     uint8_t* cntT = nullptr;     // [Ploc][Nall_pad] counts of this rank's columns over ALL rows (right operand of the column contraction)
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
     double* zbuf = nullptr;      // pre-generated right operand of the statistics GEMMs (plan.zpre)
@@ -213,13 +218,22 @@ int btf_create(const btf_config* c, btf_engine** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     e->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {
+        // the main stream carries the latency-bound kernels (band solve, row solve): highest priority, so that their CTAs
+        // are placed ahead of the queued tiles of the throughput kernels on the side streams
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        if (getenv("BTF_NO_PRIO")) hi = lo;
+        CK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&e->side[i], cudaStreamNonBlocking, lo)); }
         CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 32; ++i) CK(cudaEventCreateWithFlags(&e->ev_chunk[i / 16][i % 16], cudaEventDisableTiming));
+    if (const char* cc = getenv("BTF_COL_CHUNKS")) e->col_chunks = std::min(16, std::max(1, atoi(cc)));
     CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
     for (int i = 0; i <= PH_COUNT; ++i) CK(cudaEventCreate(&e->ph_ev[i]));
@@ -350,7 +364,7 @@ void btf_destroy(btf_engine* e) {
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
     {
-        void* i8p[] = {e->i8.planes, e->i8.colmax, e->i8.expo, e->i8.D, e->i8.bpart, e->cntT};
+        void* i8p[] = {e->i8.planes, e->i8.colmax, e->i8.expo, e->i8.D, e->i8.bpart, e->cntT, e->cnt_rowsum, e->cnt_colsum, e->guard_n, e->guard_list};
         for (void* q : i8p) if (q) cudaFree(q);
     }
     for (int i = 0; i < EVAL_SLOTS; ++i) eval_free(e->eval[i]);
@@ -366,6 +380,7 @@ void btf_destroy(btf_engine* e) {
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
     }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (int i = 0; i < 32; ++i) if (e->ev_chunk[i / 16][i % 16]) cudaEventDestroy(e->ev_chunk[i / 16][i % 16]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -665,6 +680,12 @@ int btf_get_diag(btf_engine* e, const char* name, double* host, size_t n) {
         }
         return BTF_OK;
     }
+    if (nm == "i8_guard") {
+        if (n != 2) return set_err(BTF_EINVAL, "i8_guard: 2 values");
+        host[0] = host[1] = 0.0;
+        if (e->guard_n) { int h[2]; CK(cudaMemcpy(h, e->guard_n, sizeof(h), cudaMemcpyDeviceToHost)); host[0] = h[0]; host[1] = h[1]; }
+        return BTF_OK;
+    }
     if (nm == "V_retries") {
         if (n != (size_t)e->Mloc) return set_err(BTF_EINVAL, "V_retries: expected %d values", e->Mloc);
         std::vector<int> tmp(e->Mloc);
@@ -709,59 +730,103 @@ static int begin_row_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd
     fork_side(e, fork);
     stats_i8_digits(e->i8, e->K, e->V, e->P, e->Ppad, sa);
     if (ev) cudaEventRecord(ev[0], sa);
-    pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, e->row_stats, sa);
+    pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, 0, e->row_stats, sa);
     if (pd->product != 0 && pd->product != 10) return set_err(BTF_ECUDA, "integer row statistics failed to launch");
     if (ev) cudaEventRecord(ev[1], sa);
-    pd->nsplit = stats_i8_linear(e->i8, false, e->K, e->S, e->Ppad, e->V, e->Ppad, e->nloc, sb);
+    pd->nsplit = stats_i8_linear(e->i8, false, e->K, e->S, e->Ppad, e->V, e->Ppad, e->nloc, e->i8.nsplit_b_row, e->i8.bpart, sb);
     if (ev) cudaEventRecord(ev[2], sb);
     e->launches += 4;
     return BTF_OK;
 }
 static int finish_row_stats_i8(btf_engine* e, bool fork, const I8Pending& pd) {
     join_side(e, fork);
-    stats_i8_combine(e->i8, e->K, e->nloc, e->nloc_pad, pd.product == 10, pd.nsplit, 0, e->nloc, e->row_stats, e->stream);
+    stats_i8_combine(e->i8, e->K, e->nloc, e->nloc_pad, 0, pd.product == 10, e->i8.bpart, pd.nsplit, 0, e->nloc, e->row_stats, e->stream);
     e->launches += 1;
+    if (e->guard_on) {
+        stats_i8_guard(e->i8, e->K, e->cnt, e->Ppad, e->V, e->P, e->cnt_rowsum, e->nloc, e->row_stats, e->guard_n, e->guard_list, e->stream);
+        e->launches += 2;
+    }
     return cudaGetLastError() == cudaSuccess ? BTF_OK : set_err(BTF_ECUDA, "integer row statistics failed");
 }
 
 // Columns: every rank contracts ITS columns over ALL rows (column-sharded copy of the counts, digit planes of the
 // all-gathered W), so the product block needs no exchange; the linear block is a partial sum over the local rows
 // for all columns (S stays row-sharded: it is read once either way) and is reduce-scattered (M T K doubles).
-static int begin_col_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd) {
-    cudaStream_t sa = fork ? e->side[0] : e->stream, sb = fork ? e->side[1] : e->stream;
-    cudaEvent_t* ev = (e->time_phases && timer >= 0) ? e->i8_ev[timer] : nullptr;
-    const int nco = e->nco;
-    fork_side(e, fork);
-    pd->product = 0;
-    if (ev) cudaEventRecord(ev[0], sa);
-    if (e->Ploc > 0) {
-        stats_i8_digits(e->i8, e->K, e->W, e->N, e->Nall_pad, sa);
-        if (ev) cudaEventRecord(ev[0], sa);
-        pd->product = stats_i8_product(e->i8, e->K, e->cntT, e->Nall_pad, e->Nall_pad, e->Ploc, round_up(e->Ploc, 256),
-                                       e->col_stats + (size_t)e->p0 * nco, sa);
-        if (pd->product != 0 && pd->product != 10) return set_err(BTF_ECUDA, "integer column statistics failed to launch");
-        e->launches += 3;
-    }
-    if (ev) cudaEventRecord(ev[1], sa);
-    pd->nsplit = 1;
-    if (e->nloc > 0) {
-        pd->nsplit = stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, e->W + (size_t)e->cfg.row_begin * e->K, e->nloc_pad, e->P, sb);
-        e->launches += 1;
-    } else {
-        cudaMemsetAsync(e->i8.bpart, 0, (size_t)e->P * e->K * sizeof(double), sb);
-    }
-    if (ev) cudaEventRecord(ev[2], sb);
-    return BTF_OK;
+// The V step is a pipeline over column chunks: the statistics of chunk c + 1 (tensor cores / HBM, side streams) run
+// while the latency-bound band solve of chunk c holds a few warps per SM on the main stream.
+struct ColChunks { int n = 1, cols = 0; };
+static ColChunks plan_col_chunks(const btf_engine* e, bool fork) {
+    ColChunks cc;
+    cc.n = 1; cc.cols = e->Mloc;
+    if (!fork || e->diag || e->col_chunks <= 1 || e->Mloc < 2 * e->col_chunks) return cc;
+    // chunk boundaries on multiples of 256 (j, t) positions: whole GEMM tiles, 16-byte aligned int32 rows
+    int g = 256; { int a = 256, b = e->T; while (b) { int t = a % b; a = b; b = t; } g = 256 / a; }
+    int cols = round_up((e->Mloc + e->col_chunks - 1) / e->col_chunks, g);
+    if (cols >= e->Mloc) return cc;
+    cc.cols = cols; cc.n = (e->Mloc + cols - 1) / cols;
+    return cc;
 }
-static int finish_col_stats_i8(btf_engine* e, bool fork, const I8Pending& pd) {
-    join_side(e, fork);
-    if (e->shard && nccl_reduce_scatter_cols(e->shard, e->i8.bpart, (size_t)e->T * e->K, e->stream))
-        return set_err(BTF_ENCCL, "reduce-scatter(linear block) failed: %s", nccl_shard_error());
-    if (e->Ploc > 0) {
-        stats_i8_combine(e->i8, e->K, e->Ploc, round_up(e->Ploc, 256), pd.product == 10, pd.nsplit, e->p0, e->P,
-                         e->col_stats + (size_t)e->p0 * e->nco, e->stream);
-        e->launches += 1;
+
+// band: launches the band solve of local columns [j0, j0 + ncols) on the main stream
+template <typename BandFn>
+static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
+    cudaStream_t st = e->stream;
+    cudaStream_t sa = fork ? e->side[0] : st, sb = fork ? e->side[1] : st;
+    cudaEvent_t* ev = (e->time_phases && timer >= 0) ? e->i8_ev[timer] : nullptr;
+    const int nco = e->nco, T = e->T;
+    const ColChunks cc = plan_col_chunks(e, fork);
+    const int ldd = round_up(std::max(e->Ploc, 1), 256);
+    const double* Wloc = e->W + (size_t)e->cfg.row_begin * e->K;
+    fork_side(e, fork);
+    if (ev) cudaEventRecord(ev[0], sa);
+    if (e->Ploc > 0) { stats_i8_digits(e->i8, e->K, e->W, e->N, e->Nall_pad, sa); e->launches += 2; }
+    if (ev) cudaEventRecord(ev[0], sa);
+    // linear block: sharded engines need the partial sums of ALL columns before the exchange -> one launch
+    const bool lin_whole = e->shard != nullptr || cc.n == 1;
+    if (lin_whole) {
+        if (e->nloc > 0) { stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, Wloc, e->nloc_pad, e->P, 1, e->i8.bpart, sb); e->launches++; }
+        else cudaMemsetAsync(e->i8.bpart, 0, (size_t)e->P * e->K * sizeof(double), sb);
+        if (fork) { cudaEventRecord(e->ev_join[1], sb); cudaStreamWaitEvent(st, e->ev_join[1], 0); }
+        if (e->shard && nccl_reduce_scatter_cols(e->shard, e->i8.bpart, (size_t)T * e->K, st))
+            return set_err(BTF_ENCCL, "reduce-scatter(linear block) failed: %s", nccl_shard_error());
     }
+    int product = 0, lin_split = 1;
+    for (int c = 0; c < cc.n; ++c) {
+        const int j0 = c * cc.cols, ncols = std::min(cc.cols, e->Mloc - j0);
+        const long long q0 = (long long)j0 * T;            // first local (j, t) of the chunk
+        const int np = ncols * T;
+        double* out = e->col_stats + ((size_t)e->p0 + q0) * nco;
+        if (np > 0) {
+            product = stats_i8_product(e->i8, e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->Nall_pad, np, ldd, q0, out, sa);
+            if (product != 0 && product != 10) return set_err(BTF_ECUDA, "integer column statistics failed to launch");
+            e->launches++;
+            if (!lin_whole) {
+                // a chunk's tiles alone are less than one wave: up to two splits, kept in the chunk's own region
+                lin_split = stats_i8_linear(e->i8, true, e->K, e->S + e->p0 + q0, e->Ppad, Wloc, e->nloc_pad, np, 2,
+                                            e->i8.bpart + (size_t)2 * q0 * e->K, sb);
+                e->launches++;
+            }
+        }
+        if (fork) {
+            cudaEventRecord(e->ev_chunk[0][c], sa); cudaStreamWaitEvent(st, e->ev_chunk[0][c], 0);
+            if (!lin_whole) { cudaEventRecord(e->ev_chunk[1][c], sb); cudaStreamWaitEvent(st, e->ev_chunk[1][c], 0); }
+        }
+        if (c == cc.n - 1 && ev) { cudaEventRecord(ev[1], sa); cudaEventRecord(ev[2], sb); }
+        if (np > 0) {
+            if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, st);
+            else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, st);
+            e->launches++;
+            if (e->guard_on) {
+                // (the flagged counter of the column side accumulates over the chunks of one sweep: reset by the first)
+                stats_i8_guard(e->i8, e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->W, e->N, e->cnt_colsum + q0, np, out,
+                               e->guard_n + 1, e->guard_list + std::max(e->nloc, 1) + q0, st);
+                e->launches += 2;
+            }
+        }
+        if (c == 0) phase_mark(e, PH_BAND_SOLVE);
+        if (ncols > 0) band(j0, ncols);
+    }
+    if (cc.n == 0 || e->Mloc == 0) phase_mark(e, PH_BAND_SOLVE);
     return cudaGetLastError() == cudaSuccess ? BTF_OK : set_err(BTF_ECUDA, "integer column statistics failed");
 }
 
@@ -790,6 +855,11 @@ static int ensure_i8(btf_engine* e) {
         CK(dev_alloc(&e->i8.D, z.d_elems, false));
         CK(dev_alloc(&e->i8.bpart, z.bpart_elems));
         CK(dev_alloc(&e->cntT, z.cntT_bytes));
+        CK(dev_alloc(&e->cnt_rowsum, (size_t)std::max(e->nloc, 1)));
+        CK(dev_alloc(&e->cnt_colsum, (size_t)std::max(e->Ploc, 1)));
+        CK(dev_alloc(&e->guard_n, 2));
+        CK(dev_alloc(&e->guard_list, (size_t)std::max(e->nloc, 1) + std::max(e->Ploc, 1)));
+        e->guard_on = getenv("BTF_I8_NO_GUARD") == nullptr;
         e->i8.nsplit_b_row = z.nsplit_b_row;
     }
     if (!e->shard) {
@@ -811,6 +881,10 @@ static int ensure_i8(btf_engine* e) {
         if (rc) return set_err(BTF_ENCCL, "exchange of the count blocks failed: %s", nccl_shard_error());
         if (ce != cudaSuccess) return set_err(BTF_ECUDA, "exchange of the count blocks: %s", cudaGetErrorString(ce));
     }
+    // count sums of every local row and every owned (j, t): the error bound of the fixed-point block is 2^(e_c - 55) n_m
+    stats_i8_count_rows(e->cnt, e->Ppad, e->nloc, e->Ppad, e->cnt_rowsum, st);
+    stats_i8_count_rows(e->cntT, e->Nall_pad, e->Ploc, e->Nall_pad, e->cnt_colsum, st);
+    e->launches += 2;
     // one eager pass so that every kernel attribute is set before a graph capture
     e->i8_on = true;
     I8Pending pd;
@@ -818,8 +892,7 @@ static int ensure_i8(btf_engine* e) {
         int rc = begin_row_stats_i8(e, false, -1, &pd); if (rc) { e->i8_on = false; return rc; }
         rc = finish_row_stats_i8(e, false, pd); if (rc) { e->i8_on = false; return rc; }
     }
-    { int rc = begin_col_stats_i8(e, false, -1, &pd); if (rc) { e->i8_on = false; return rc; }
-      rc = finish_col_stats_i8(e, false, pd); if (rc) { e->i8_on = false; return rc; } }
+    { int rc = col_step_i8(e, false, -1, [](int, int) {}); if (rc) { e->i8_on = false; return rc; } }
     CK(cudaStreamSynchronize(st));
     free_graph(e);
     return BTF_OK;
@@ -849,7 +922,7 @@ static int enqueue_sweep(btf_engine* e) {
     // (tensor-core product block | HBM-bound linear block) while the hyper-parameter steps run on the main stream.
     const bool doW = (mask & BTF_SAMPLE_W) && e->nloc > 0;
     const bool fork = e->overlap && e->i8_on && !e->time_phases;
-    I8Pending pend_row, pend_col;
+    I8Pending pend_row;
     if (fork && doW) { int rc = begin_row_stats_i8(e, true, 0, &pend_row); if (rc) return rc; }
 
     if (c.likelihood == BTF_NEGBINOMIAL) {
@@ -966,13 +1039,37 @@ static int enqueue_sweep(btf_engine* e) {
     }
     // ---- V | rest
     if (mask & BTF_SAMPLE_V) {
-        int nsplit = e->plan_col.nsplit;
+        BandSolveArgs ba;
+        ba.stats = e->col_stats; ba.nsplit = 1; ba.split_stride = e->plan_col.out_elems_per_split;
+        ba.col_begin = c.col_begin; ba.ncols_loc = e->Mloc; ba.T = e->T; ba.K = e->K; ba.order = e->order; ba.RD = e->RD;
+        ba.homoskedastic = gauss ? 1 : 0; ba.scal = e->scal; ba.Tau2 = e->Tau2;
+        ba.prior_clip = c.clip_prior_precision ? c.stability : 0.0;
+        ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
+        ba.V = e->V; ba.z_inject = inj(e, "z_V"); ba.seed = c.seed;
+        ba.work_L = e->work_L; ba.work_y = e->work_y;
+        ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
+        ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
+        const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
+        ba.diag_band = diag_get(e, "V_band", bn);
+        ba.diag_chol = diag_get(e, "V_chol", bn);
+        ba.diag_mean = diag_get(e, "V_mean", (size_t)e->P * e->K);
+        ba.diag_retries = e->diag_retries;
+        ba.resid_partials = gauss ? e->resid_partials + c.col_begin : nullptr;
+        // the band solve of local columns [j0, j0 + ncols): every per-column array of the kernel is indexed from its base
+        auto band = [&](int j0, int ncols) {
+            BandSolveArgs b = ba;
+            b.col_begin = c.col_begin + j0; b.ncols_loc = ncols;
+            b.work_L = ba.work_L + (size_t)j0 * ba.work_L_stride; b.work_y = ba.work_y + (size_t)j0 * ba.work_y_stride;
+            if (b.resid_partials) b.resid_partials += j0;
+            if (b.diag_retries) b.diag_retries += j0;
+            launch_band_solve(b, st); e->launches++;
+        };
         if (e->i8_on) {
-            { int rc = begin_col_stats_i8(e, fork, 1, &pend_col); if (rc) return rc; }
-            { int rc = finish_col_stats_i8(e, fork, pend_col); if (rc) return rc; }
-            nsplit = 1;
             e->col_collapsed = false;
+            int rc = col_step_i8(e, fork, 1, band);      // statistics and band solves, pipelined over column chunks
+            if (rc) return rc;
         } else {
+            int nsplit = e->plan_col.nsplit;
             launch_stats(e->plan_col, true, !gauss, wt, e->S, e->W + (size_t)c.row_begin * e->K, e->nloc_pad, e->Ppad, e->P,
                          e->col_stats, e->zbuf, st);
             e->launches += e->plan_col.zpre ? 2 : 1;
@@ -993,26 +1090,9 @@ static int enqueue_sweep(btf_engine* e) {
             } else {
                 e->col_collapsed = false;
             }
-        }
-        phase_mark(e, PH_BAND_SOLVE);
-        if (e->Mloc > 0) {
-            BandSolveArgs ba;
-            ba.stats = e->col_stats; ba.nsplit = nsplit; ba.split_stride = e->plan_col.out_elems_per_split;
-            ba.col_begin = c.col_begin; ba.ncols_loc = e->Mloc; ba.T = e->T; ba.K = e->K; ba.order = e->order; ba.RD = e->RD;
-            ba.homoskedastic = gauss ? 1 : 0; ba.scal = e->scal; ba.Tau2 = e->Tau2;
-            ba.prior_clip = c.clip_prior_precision ? c.stability : 0.0;
-            ba.pm_ptr = e->pm_ptr; ba.pm_row = e->pm_row; ba.pm_coef = e->pm_coef;
-            ba.V = e->V; ba.z_inject = inj(e, "z_V"); ba.seed = c.seed;
-            ba.work_L = e->work_L; ba.work_y = e->work_y;
-            ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
-            ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
-            const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
-            ba.diag_band = diag_get(e, "V_band", bn);
-            ba.diag_chol = diag_get(e, "V_chol", bn);
-            ba.diag_mean = diag_get(e, "V_mean", (size_t)e->P * e->K);
-            ba.diag_retries = e->diag_retries;
-            ba.resid_partials = gauss ? e->resid_partials + c.col_begin : nullptr;
-            launch_band_solve(ba, st); e->launches++;
+            ba.nsplit = nsplit;
+            phase_mark(e, PH_BAND_SOLVE);
+            if (e->Mloc > 0) band(0, e->Mloc);
         }
         phase_mark(e, PH_COMM);
         if (e->shard) {

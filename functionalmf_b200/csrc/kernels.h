@@ -60,11 +60,17 @@ void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, 
 // the four stages of the integer path (engine: tensor-core contraction and HBM-bound linear block on separate streams)
 void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows, int kdim_pad, cudaStream_t st);
 int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
-                     double* out, cudaStream_t st);     // 0: int32 planes in w.D, 10: fused epilogue wrote out, else error
+                     long long d_off, double* out, cudaStream_t st);     // 0: int32 planes in w.D + d_off, 10: fused epilogue wrote out, else error
 int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S, long long lds, const double* F,
-                    int kdim_pad, int m_valid, cudaStream_t st);     // returns the split count of w.bpart
-void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, bool product_done, int nsplit_b,
-                      long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st);
+                    int kdim_pad, int m_valid, int max_split, double* out, cudaStream_t st);     // returns the split count of `out`
+void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, long long d_off, bool product_done,
+                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st);
+// element-wise guard of the fixed-point product block: cntsum[m] = sum_k B[m][k] (once per data set); rows whose
+// diagonal entries cannot be guaranteed to `BTF_I8_GUARD_TOL` (default 1e-12) relative are listed in flagged[0..*nflag)
+// and their product block is recomputed in FP64 (B: counts [m][ldb], F: factor rows [f_rows][K])
+void stats_i8_count_rows(const uint8_t* B, long long ldb, int m_valid, int kdim_pad, unsigned* cntsum, cudaStream_t st);
+void stats_i8_guard(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, const double* F, int f_rows,
+                    const unsigned* cntsum, int m_valid, double* out, int* nflag, int* flagged, cudaStream_t st);
 // out[m][L+K] (one split) for count weights: exact product block + FP64 linear block, all stages on one stream
 int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
                     long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,

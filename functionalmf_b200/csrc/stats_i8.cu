@@ -244,6 +244,87 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
     }
 }
 
+// ---- element-wise guard of the fixed-point product block.
+// Every entry of Z is rounded to a multiple of 2^(e_c - 54), so |out[m][c] - exact| <= 2^(e_c - 55) n_m with
+// n_m = sum_k cnt[m][k].  That is 2^-55 relative to the COLUMN maximum: fine normwise, but a row whose observed cells
+// all sit where |Z| is far below the column maximum (structured missingness + badly scaled factors) gets a large
+// RELATIVE error.  The diagonal columns c = (k, k) are sums of non-negative terms, so bound / out[m][(k,k)] is the true
+// relative accuracy of the row's precision matrix; rows where it exceeds `tol` are listed and recomputed in plain FP64.
+__global__ void __launch_bounds__(256) i8_guard_kernel(const double* __restrict__ out, int nco, int m_valid, int K,
+                                                       const int* __restrict__ expo, const unsigned* __restrict__ cntsum,
+                                                       double tol, int* __restrict__ nflag, int* __restrict__ flagged) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= m_valid) return;
+    const double n_m = (double)cntsum[m];
+    bool bad = false;
+    for (int k = 0; k < K; ++k) {
+        const int c = k * (k + 3) / 2;                          // packed index of (k, k)
+        const double bound = scalbn(n_m, expo[c] - (FIXBITS + 1));
+        const double v = out[(long long)m * nco + c];
+        bad = bad || (bound > tol * v);
+    }
+    if (bad) flagged[atomicAdd(nflag, 1)] = m;
+}
+
+// out[m][c] (c < L) = sum_k B[m][k] F[k,k1] F[k,k2] in FP64 for the listed rows: one CTA per row (grid-stride over the
+// list), 128-row slabs of F in shared memory, thread t owns the packed columns t, t + 256, ...
+template <int MAXC>
+__global__ void __launch_bounds__(256) i8_fallback_kernel(const uint8_t* __restrict__ B, long long ldb, const double* __restrict__ F,
+                                                          int f_rows, int K, int L, const int* __restrict__ nflag,
+                                                          const int* __restrict__ flagged, double* __restrict__ out, int nco) {
+    extern __shared__ __align__(16) double fsm[];               // [128][K] + 128 counts
+    double* Fs = fsm;
+    double* Cs = fsm + 128 * K;
+    const int n = *nflag;
+    int k1[MAXC], k2[MAXC];
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) { k1[q] = k2[q] = 0; const int c = threadIdx.x + 256 * q; if (c < L) pair_of(c, k1[q], k2[q]); }
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const int m = flagged[it];
+        double acc[MAXC][2];
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) acc[q][0] = acc[q][1] = 0.0;
+        for (int r0 = 0; r0 < f_rows; r0 += 128) {
+            const int nr = min(128, f_rows - r0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nr * K; e += 256) Fs[e] = F[(long long)r0 * K + e];
+            for (int e = threadIdx.x; e < 128; e += 256) Cs[e] = e < nr ? (double)B[(long long)m * ldb + r0 + e] : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < MAXC; ++q) {
+                if (threadIdx.x + 256 * q < L) {
+                    for (int r = 0; r + 1 < nr + 1; r += 2) {
+                        const double c0 = Cs[r], c1 = (r + 1 < nr) ? Cs[r + 1] : 0.0;
+                        if (c0 != 0.0) acc[q][0] = fma(c0, Fs[r * K + k1[q]] * Fs[r * K + k2[q]], acc[q][0]);
+                        if (c1 != 0.0) acc[q][1] = fma(c1, Fs[(r + 1) * K + k1[q]] * Fs[(r + 1) * K + k2[q]], acc[q][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+            const int c = threadIdx.x + 256 * q;
+            if (c < L) out[(long long)m * nco + c] = acc[q][0] + acc[q][1];
+        }
+    }
+}
+
+// cntsum[m] = sum_k B[m][k] (uint8 rows of length kdim, 16-byte aligned): one warp per row
+__global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t* __restrict__ B, long long ldb, int m_valid, int kdim,
+                                                         unsigned* __restrict__ cntsum) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= m_valid) return;
+    const uint4* row = reinterpret_cast<const uint4*>(B + (long long)m * ldb);
+    unsigned s = 0;
+    for (int q = lane; q < kdim / 16; q += 32) {
+        const uint4 v = row[q];
+        s += __vsadu4(v.x, 0u) + __vsadu4(v.y, 0u) + __vsadu4(v.z, 0u) + __vsadu4(v.w, 0u);     // sum of the 4 bytes of each word
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) cntsum[m] = s;
+}
+
 // dst[p][i] = src[i][p]  (uint8), 32 x 32 tiles
 __global__ void __launch_bounds__(256) transpose_u8_kernel(const uint8_t* __restrict__ src, long long lds, int rows, int cols,
                                                            uint8_t* __restrict__ dst, long long ldd) {
@@ -299,7 +380,7 @@ void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, int nall_pad
     s->d_elems = (size_t)(NPLANES * L * nd);
     s->cntT_bytes = (size_t)std::max(ploc, 1) * nall_pad;
     s->nsplit_b_row = 64;            // upper bound of the split count of the row-variant linear block (buffer size)
-    s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)P * K);
+    s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)2 * P * K);   // columns: up to two splits per chunk
     s->L = (int)L;
 }
 
@@ -324,7 +405,7 @@ void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows
 // 2. exact product block on the tensor cores: D[(8 c + s)][m] = sum_k d_s[k, c] B[m][k], m < m_valid (B = counts, K-major)
 //    returns 0 (int32 planes in w.D), 10 (fused epilogue wrote out[m][c] directly), else an error
 int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
-                     double* out, cudaStream_t st) {
+                     long long d_off, double* out, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
     const bool force_fused = getenv("BTF_STATS_I8_FUSED") != nullptr && getenv("BTF_STATS_I8_NOFUSED") == nullptr;
     // (measured on C2: the fused epilogue's FP64 stores are not hidden under the next tile, 0.29 + 0.50 ms against
@@ -335,13 +416,13 @@ int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long
         if (rc == 0) return 10;
         if (rc > 1) return 1;
     }
-    return launch_i8gemm(w.planes, kdim_pad, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D, m_pad, st)
-               ? 1 : 0;
+    return launch_i8gemm(w.planes, kdim_pad, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D + d_off,
+                         m_pad, st) ? 1 : 0;
 }
 
 // 3. linear block in FP64: bpart[split][m][j] = sum_k S[m, k] F[k, j] over the split's k range; returns the split count
 int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S, long long lds, const double* F,
-                    int kdim_pad, int m_valid, cudaStream_t st) {
+                    int kdim_pad, int m_valid, int max_split, double* out, cudaStream_t st) {
     const int nchunks = kdim_pad / 32;
     const int m_tiles = (m_valid + 127) / 128;
     // BTF_SF_RESIDENT=1: one CTA per SM with a small shared-memory footprint, dealt (tile, split) items round-robin,
@@ -355,28 +436,45 @@ int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S,
     if (m_tiles < target) {
         nsplit = target / m_tiles;       // never a partial last wave
         if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
-        if (nsplit > (trans ? 1 : w.nsplit_b_row)) nsplit = trans ? 1 : w.nsplit_b_row;
+        if (nsplit > max_split) nsplit = max_split;
     }
     { const int cps = (nchunks + nsplit - 1) / nsplit; nsplit = (nchunks + cps - 1) / cps; }
-    if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
-    else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
-    else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, w.bpart, st); }
+    if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); }
+    else if (K <= 16) { if (trans) launch_sf_t<16, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); else launch_sf_t<16, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); }
+    else { if (trans) launch_sf_t<32, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); else launch_sf_t<32, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); }
     return nsplit;
 }
 
 // 4. recombination of the int32 planes (skipped when the fused epilogue already wrote them) and the sum of the
 //    linear-block partials: out[m][0..L) from D, out[m][L..L+K) from bpart[split][bpart_m0 + m][.] (row pitch of a
 //    split = bpart_rows)
-void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, bool product_done, int nsplit_b,
-                      long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st) {
+void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, long long d_off, bool product_done,
+                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
     const int ncy = (L + 31) / 32;
     if (product_done)
-        i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D, m_pad, w.expo, w.bpart, nsplit_b, m_valid, L, K, out, ncy,
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D + d_off, m_pad, w.expo, bpart, nsplit_b, m_valid, L, K, out, ncy,
                                                                        bpart_m0, bpart_rows);
     else
-        i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D, m_pad, w.expo, w.bpart, nsplit_b, m_valid, L, K, out, 0,
+        i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D + d_off, m_pad, w.expo, bpart, nsplit_b, m_valid, L, K, out, 0,
                                                                              bpart_m0, bpart_rows);
+}
+
+// 5. element-wise guard + FP64 recomputation of the rows it lists (2 small launches; see i8_guard_kernel)
+void stats_i8_count_rows(const uint8_t* B, long long ldb, int m_valid, int kdim_pad, unsigned* cntsum, cudaStream_t st) {
+    if (m_valid > 0) count_rows_kernel<<<(m_valid + 7) / 8, 256, 0, st>>>(B, ldb, m_valid, kdim_pad, cntsum);
+}
+void stats_i8_guard(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, const double* F, int f_rows,
+                    const unsigned* cntsum, int m_valid, double* out, int* nflag, int* flagged, cudaStream_t st) {
+    if (m_valid <= 0) return;
+    const int L = K * (K + 1) / 2, nco = L + K;
+    static const double tol = getenv("BTF_I8_GUARD_TOL") ? atof(getenv("BTF_I8_GUARD_TOL")) : 1e-12;
+    cudaMemsetAsync(nflag, 0, sizeof(int), st);
+    i8_guard_kernel<<<(m_valid + 255) / 256, 256, 0, st>>>(out, nco, m_valid, K, w.expo, cntsum, tol, nflag, flagged);
+    const size_t smem = (size_t)(128 * K + 128) * sizeof(double);
+    const int grid = std::min(m_valid, 592);
+    if (L <= 256) i8_fallback_kernel<1><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, nflag, flagged, out, nco);
+    else i8_fallback_kernel<3><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, nflag, flagged, out, nco);
 }
 
 // All four stages on one stream.
@@ -387,12 +485,12 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
                     cudaStream_t st) {
     stats_i8_digits(w, K, F, f_rows, kdim_pad, st);
     if (w.ev[0]) cudaEventRecord(w.ev[0], st);
-    const int pr = stats_i8_product(w, K, B, ldb, kdim_pad, m_valid, m_pad, out, st);
+    const int pr = stats_i8_product(w, K, B, ldb, kdim_pad, m_valid, m_pad, 0, out, st);
     if (pr != 0 && pr != 10) return 1;
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
-    const int nsplit = stats_i8_linear(w, trans, K, S, lds, F, kdim_pad, m_valid, st);
+    const int nsplit = stats_i8_linear(w, trans, K, S, lds, F, kdim_pad, m_valid, trans ? 1 : w.nsplit_b_row, w.bpart, st);
     if (w.ev[2]) cudaEventRecord(w.ev[2], st);
-    stats_i8_combine(w, K, m_valid, m_pad, pr == 10, nsplit, 0, m_valid, out, st);
+    stats_i8_combine(w, K, m_valid, m_pad, 0, pr == 10, w.bpart, nsplit, 0, m_valid, out, st);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

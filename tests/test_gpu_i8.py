@@ -134,3 +134,82 @@ def test_sweep_matches_the_fp64_path(shape, gemm_mode):
     for k in ('W', 'V', 'Tau2'):
         assert np.max(np.abs(a[k] - b[k])) <= 1e-8 * np.max(np.abs(b[k])), k
     assert a['nu2'] == pytest.approx(b['nu2'], rel=1e-9) and a['sigma2'] == pytest.approx(b['sigma2'], rel=1e-9)
+
+
+def _exact_product_block(F, cnt):
+    """sum_k cnt[m,k] F[k,k1] F[k,k2] in extended precision (packed lower triangle), as float64."""
+    K = F.shape[1]
+    il = np.tril_indices(K)
+    Z = (F[:, il[0]].astype(np.longdouble) * F[:, il[1]].astype(np.longdouble))
+    return (cnt.astype(np.longdouble) @ Z).astype(np.float64)
+
+
+def _guard_case(no_guard):
+    """Block-structured missingness + factor scales spanning 1e6: rows >= 200 observe only the
+    columns whose V is 1e-6 times smaller, so their statistics sit 1e-12 below the column maxima that fix the
+    fixed-point scale; same construction transposed for the column statistics."""
+    from functionalmf_b200 import _lib as L
+    N, M, T, R, K = 256, 8, 16, 2, 16
+    rs = np.random.RandomState(4)
+    V = rs.normal(size=(M, T, K)); V[4:] *= 1e-6
+    W = rs.normal(size=(N, K)); W[128:] *= 1e-6
+    Y = rs.normal(size=(N, M, T, R))
+    Y[rs.random_sample(Y.shape) < 0.2] = np.nan
+    Y[200:, :4] = np.nan                  # rows 200.. see only the small columns
+    Y[:128, 6:] = np.nan                  # columns 6.. see only the small rows
+    for k in ('BTF_STATS_FORCE_I8', 'BTF_STATS_NO_I8', 'BTF_I8_NO_GUARD') + GEMM_MODES:
+        os.environ.pop(k, None)
+    os.environ['BTF_STATS_FORCE_I8'] = '1'
+    if no_guard:
+        os.environ['BTF_I8_NO_GUARD'] = '1'
+    from functionalmf_b200.engine import Engine
+    eng = Engine(N, M, T, nembeds=K, tf_order=2, seed=5, use_graph=0)
+    try:
+        eng.set_data_gaussian(Y)
+        eng.init_state(127)
+        eng.set('W', W); eng.set('V', V)
+        for k, v in dict(lam2=0.7, sigma2=0.9, nu2=1.1).items():
+            eng.set(k, [v])
+        eng.enable_diag(True)
+        cnt = (~np.isnan(Y)).sum(axis=-1).reshape(N, M * T)
+        Lp = K * (K + 1) // 2
+        dg = np.array([k * (k + 3) // 2 for k in range(K)])
+        il = np.tril_indices(K)
+        out = {}
+        # columns first (V | rest with the W set above), then rows (W | rest with the V just drawn replaced by ours)
+        eng.set_sample_mask(L.SAMPLE_V)
+        eng.sweep(1)
+        cols = eng.diag('col_stats')[:, :Lp]
+        out['col_flagged'] = int(eng.diag('i8_guard')[1])
+        want = _exact_product_block(W, cnt.T)
+        out['col_rel'] = np.abs(cols[:, dg] / want[:, dg] - 1.0)
+        sc = np.sqrt(want[:, dg][:, il[0]] * want[:, dg][:, il[1]])
+        out['col_off'] = np.abs(cols - want) / sc
+        eng.set('V', V)
+        eng.set_sample_mask(L.SAMPLE_W)
+        eng.sweep(1)
+        rows = eng.diag('row_stats')[:, :Lp]
+        out['row_flagged'] = int(eng.diag('i8_guard')[0])
+        want = _exact_product_block(V.reshape(M * T, K), cnt)
+        out['row_rel'] = np.abs(rows[:, dg] / want[:, dg] - 1.0)
+        sc = np.sqrt(want[:, dg][:, il[0]] * want[:, dg][:, il[1]])
+        out['row_off'] = np.abs(rows - want) / sc
+        return out
+    finally:
+        eng.close()
+        for k in ('BTF_STATS_FORCE_I8', 'BTF_I8_NO_GUARD'):
+            os.environ.pop(k, None)
+
+
+def test_elementwise_guard_keeps_badly_scaled_rows_accurate():
+    """Element-wise (not normwise) accuracy of the integer path: every diagonal entry of every row / (j,t) statistic to
+    1e-10 relative, every off-diagonal entry to 1e-10 of sqrt(d1 d2), although the fixed-point scale is set by column
+    maxima 1e12 times larger.  The guard must list exactly the rows / columns that only see the small factors, and
+    without it (BTF_I8_NO_GUARD=1) the same data must miss the bound - the test has teeth."""
+    g = _guard_case(no_guard=False)
+    assert g['row_flagged'] == 56 and g['col_flagged'] == 2 * 16          # rows 200..255; columns j = 6, 7 at every t
+    assert g['row_rel'].max() < 1e-10 and g['col_rel'].max() < 1e-10
+    assert g['row_off'].max() < 1e-10 and g['col_off'].max() < 1e-10
+    bad = _guard_case(no_guard=True)
+    assert bad['row_flagged'] == 0 and bad['col_flagged'] == 0
+    assert bad['row_rel'].max() > 1e-8 and bad['col_rel'].max() > 1e-8
