@@ -63,32 +63,50 @@ __device__ __forceinline__ bool leq_exp(double u, double x) {
     return u <= exp(x);
 }
 
-// Truncated inverse-Gaussian(1/Z, 1) on (0, t].  `u0` is a spare uniform the caller already
-// holds (used for the first acceptance test, so the common path costs one Philox call).
-__device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
+// A decision uniform is consumed 32 bits at a time: its leading word decides everything but a borderline
+// (probability ~1e-4) case, for which 32 more bits are drawn - the comparison is the one a 64-bit uniform gives,
+// at half a Philox call per decision.
+__device__ __forceinline__ double refine_uniform(Rng& rng, uint32_t hi) {
+    const uint4 q = rng.next4();
+    return ((double)(((unsigned long long)hi << 32) | q.x) + 0.5) * (1.0 / 18446744073709551616.0);
+}
+__device__ __forceinline__ bool leq_exp32(Rng& rng, uint32_t hi, double x) {
+    const float ef = __expf((float)x), uf = ((float)hi + 0.5f) * 2.3283064365386963e-10f;
+    if (uf < ef * 0.9999f - 1e-30f) return true;
+    if (uf > ef * 1.0001f + 1e-30f) return false;
+    return refine_uniform(rng, hi) <= exp(x);
+}
+
+// Truncated inverse-Gaussian(1/Z, 1) on (0, t].  `u0` is a spare value uniform and `a_hi` a spare 32-bit decision
+// word the caller already holds, so the common path costs no Philox call of its own.
+//
+// mu = 1/Z > t: Polson-Scott-Windle propose X = t / (1 + t E)^2 with E accepted from Exp(1) with probability
+// exp(-t E^2 / 2), i.e. E ~ N(-1/t, 1/t) truncated to E > 0.  With Y = sqrt(t) (E + 1/t) that is X = 1 / Y^2 for a
+// standard normal Y truncated to Y > 1/sqrt(t) - the Levy law cut at t - so the inner rejection loop (acceptance
+// 0.69 per lane: a warp iterated until its slowest lane got through, ~4 rounds of Philox + log + exp each) is
+// replaced by ONE inversion Y = Phi^-1(U Phi(-1/sqrt(t))): same distribution, no loop, no divergence.
+__device__ double pg_rtigauss(Rng& rng, double Z, double u0, uint32_t a_hi) {
     const double t = PG_TRUNC;
-    bool have_u0 = true;
-    if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0): exponential-tail proposal
+    bool first = true;
+    if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0)
+        const double QT = 0.10564977366685535;      // Phi(-1.25), 1/sqrt(0.64) = 1.25
+        const double hz2 = -0.5 * Z * Z;
         for (int it = 0; it < 10000; ++it) {
-            double e1 = 0.0;
-            for (int k = 0; k < 10000; ++k) {
-                const double2 u = rng.uniform2();
-                e1 = -log(u.x);
-                // E1^2 <= 2 E2 / t  with E2 = -log(u.y)   <=>   u.y <= exp(-t E1^2 / 2)
-                if (leq_exp(u.y, -0.5 * t * e1 * e1)) break;
-            }
-            const double X = t / ((1.0 + t * e1) * (1.0 + t * e1));
-            const double ua = have_u0 ? u0 : rng.uniform();
-            have_u0 = false;
-            if (leq_exp(ua, -0.5 * Z * Z * X)) return X;
+            double uv;
+            uint32_t ah;
+            if (first) { uv = u0; ah = a_hi; first = false; }
+            else { const uint4 r = rng.next4(); uv = Rng::to_unit(r.x, r.y); ah = r.z; }
+            const double Y = normcdfinv(fmax(uv, 1e-300) * QT);   // < -1.25
+            const double X = 1.0 / (Y * Y);                         // <= t
+            if (leq_exp32(rng, ah, hz2 * X)) return X;
         }
         return t;
     }
     const double mu = 1.0 / Z;
     for (int it = 0; it < 10000; ++it) {
         double2 nu = rng.normal2();
-        double ua = have_u0 ? u0 : rng.uniform();
-        have_u0 = false;
+        double ua = first ? u0 : rng.uniform();
+        first = false;
         double Y = nu.x * nu.x;
         double X = mu + 0.5 * mu * mu * Y - 0.5 * mu * sqrt(4.0 * mu * Y + (mu * Y) * (mu * Y));
         if (ua > mu / (mu + X)) X = mu * mu / X;
@@ -97,30 +115,30 @@ __device__ double pg_rtigauss(Rng& rng, double Z, double u0) {
     return t;
 }
 
-// One PG(1, z) draw (Devroye / Polson-Scott-Windle alternating series).  The first
+// One PG(1, z) draw (Devroye / Polson-Scott-Windle alternating series): ONE Philox call on the common path - 53
+// bits for the proposal's value, 32 bits for each of the two decisions (refined when borderline).  The first
 // acceptance test  U a_0 <= a_0 - a_1  only needs the ratio a_1 / a_0 = 3 exp(-4/x) (x <= t)
 // or 3 exp(-pi^2 x) (x > t); the full coefficients are evaluated only on the rare (< 0.6 %)
 // continuation of the series.
 __device__ double pg_one(Rng& rng, const PgTilt& c) {
     for (int it = 0; it < 10000; ++it) {
         const uint4 r = rng.next4();
-        const double u1 = Rng::to_unit(r.x, r.y), u2 = Rng::to_unit(r.z, r.w);
+        const double u1 = Rng::to_unit(r.x, r.y);
         double X;
         if (u1 < c.pmass) X = PG_TRUNC - log(u1 * c.inv_p) * c.inv_fz;    // u1 / pmass is U(0,1) given the branch
-        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) * c.inv_q);
+        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) * c.inv_q, r.z);
         const double arg = X > PG_TRUNC ? -PG_PI * PG_PI * X : -4.0 / X;
-        // u2 <= 1 - 3 exp(arg): FP32 screen (the threshold is within 2e-2 of 1), FP64 when borderline
+        // u2 <= 1 - 3 exp(arg): FP32 screen (the threshold is within 2e-2 of 1), full precision when borderline
         const float thr = 1.0f - 3.0f * __expf((float)arg);
-        const float u2f = (float)u2;
-        bool accept;
-        if (u2f < thr - 2e-6f) accept = true;
-        else if (u2f > thr + 2e-6f) accept = false;
-        else accept = u2 <= 1.0 - 3.0 * exp(arg);
-        if (accept) return 0.25 * X;
+        const float u2f = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;
+        if (u2f < thr - 2e-6f) return 0.25 * X;
+        const double u2 = refine_uniform(rng, r.w);
+        if (u2f <= thr + 2e-6f && u2 <= 1.0 - 3.0 * exp(arg)) return 0.25 * X;
         // continue the series from n = 2 with explicit coefficients
         double S = pg_acoef(0, X);
         const double Y = u2 * S;
         S -= pg_acoef(1, X);
+        if (Y <= S) return 0.25 * X;               // (the screen above is a bound on the same test)
         for (int n = 2; n < 400; ++n) {
             if (n & 1) { S -= pg_acoef(n, X); if (Y <= S) return 0.25 * X; }
             else { S += pg_acoef(n, X); if (Y > S) break; }
