@@ -63,7 +63,7 @@ struct btf_engine {
     cudaStream_t side[2] = {nullptr, nullptr};   // forked inside a sweep: tensor-core product block | HBM-bound linear block
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[2][16] = {{nullptr}};   // per column chunk of the V step: product block done | linear block done
-    int col_chunks = 4;          // BTF_COL_CHUNKS: the V step runs as a pipeline over this many column chunks
+    int col_chunks = 1;          // BTF_COL_CHUNKS: the V step can run as a pipeline over column chunks (off by default: see DESIGN.md)
     bool overlap = true;         // BTF_NO_OVERLAP=1: everything on one stream (A/B runs)
     // state
     double *W = nullptr, *V = nullptr, *Tau2 = nullptr, *Tau2_a = nullptr, *Tau2_b = nullptr, *Tau2_c = nullptr;
@@ -782,14 +782,17 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
     if (e->Ploc > 0) { stats_i8_digits(e->i8, e->K, e->W, e->N, e->Nall_pad, sa); e->launches += 2; }
     if (ev) cudaEventRecord(ev[0], sa);
     // linear block: sharded engines need the partial sums of ALL columns before the exchange -> one launch
+    // (on the side stream when forked; in the serial mode it is issued after the product block, see below)
     const bool lin_whole = e->shard != nullptr || cc.n == 1;
-    if (lin_whole) {
+    auto linear_whole = [&]() -> int {
         if (e->nloc > 0) { stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, Wloc, e->nloc_pad, e->P, 1, e->i8.bpart, sb); e->launches++; }
         else cudaMemsetAsync(e->i8.bpart, 0, (size_t)e->P * e->K * sizeof(double), sb);
         if (fork) { cudaEventRecord(e->ev_join[1], sb); cudaStreamWaitEvent(st, e->ev_join[1], 0); }
         if (e->shard && nccl_reduce_scatter_cols(e->shard, e->i8.bpart, (size_t)T * e->K, st))
             return set_err(BTF_ENCCL, "reduce-scatter(linear block) failed: %s", nccl_shard_error());
-    }
+        return BTF_OK;
+    };
+    if (lin_whole && fork) { int rc = linear_whole(); if (rc) return rc; }
     int product = 0, lin_split = 1;
     for (int c = 0; c < cc.n; ++c) {
         const int j0 = c * cc.cols, ncols = std::min(cc.cols, e->Mloc - j0);
@@ -811,7 +814,9 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
             cudaEventRecord(e->ev_chunk[0][c], sa); cudaStreamWaitEvent(st, e->ev_chunk[0][c], 0);
             if (!lin_whole) { cudaEventRecord(e->ev_chunk[1][c], sb); cudaStreamWaitEvent(st, e->ev_chunk[1][c], 0); }
         }
-        if (c == cc.n - 1 && ev) { cudaEventRecord(ev[1], sa); cudaEventRecord(ev[2], sb); }
+        if (c == cc.n - 1 && ev) cudaEventRecord(ev[1], sa);
+        if (lin_whole && !fork) { int rc = linear_whole(); if (rc) return rc; }     // serial mode: one chunk
+        if (c == cc.n - 1 && ev) cudaEventRecord(ev[2], sb);
         if (np > 0) {
             if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, st);
             else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, st);
