@@ -995,7 +995,6 @@ static int enqueue_sweep(btf_engine* e) {
             hs.col_begin = c.col_begin; hs.col_end = c.col_end;
             launch_tau2(hs, st);
             if (c.col_end != e->M) { hs.col_begin = e->M - 1; hs.col_end = e->M; launch_tau2(hs, st); e->launches++; }
-            e->tau_stale = true;
         } else {
             launch_tau2(ha, st);
         }
@@ -1165,6 +1164,8 @@ static int build_graph(btf_engine* e) {
 
 // one sweep, by graph replay when the sequence is static
 static int one_sweep(btf_engine* e) {
+    // (set here, not while enqueueing: a graph replay does not run the enqueue code)
+    if (e->tau_sharded && (e->cfg.sample_mask & BTF_SAMPLE_TAU2)) e->tau_stale = true;
     if (graph_ok(e)) {
         if (!e->graph_exec) { int rc = build_graph(e); if (rc) return rc; }
         CK(cudaGraphLaunch(e->graph_exec, e->stream));
@@ -1230,6 +1231,7 @@ int btf_time_phases(btf_engine* e, int32_t nsweeps, double* ms_out, int32_t npha
     for (int i = 0; i < nphases; ++i) ms_out[i] = 0.0;
     e->time_phases = true;
     for (int s = 0; s < nsweeps; ++s) {
+        if (e->tau_sharded && (e->cfg.sample_mask & BTF_SAMPLE_TAU2)) e->tau_stale = true;
         rc = enqueue_sweep(e);
         if (rc) break;
         CK(cudaStreamSynchronize(e->stream));

@@ -4,9 +4,10 @@
 //
 // Why it exists: the sufficient-statistic contractions out[m, l] = sum_k cnt[m, k] Z[k, l] have an
 // INTEGER left operand (cnt = number of observed replicates, 0..R).  Writing every column of Z as a
-// fixed-point number  Z[k, l] = scale_l 2^-55 sum_s 128^s d_s[k, l]  with signed 7-bit digits d_s turns
-// the FP64 contraction into 8 int8 x int8 -> int32 contractions whose results are EXACT; the digits
-// are recombined in 128-bit integer arithmetic and rounded once (stats_i8.cu).  The FP64 pipe of the
+// fixed-point number  Z[k, l] = scale_l 2^-54 sum_s 256^s d_s[k, l]  with signed 8-bit digits d_s turns
+// the FP64 contraction into 7 int8 x int8 -> int32 contractions whose results are EXACT; the digits
+// are recombined in integer arithmetic and rounded once (stats_i8.cu).  This file is the single-CTA 128 x 256 kernel
+// with split-K (shapes with few tiles, the raw GEMM test hook); the large contractions run in i8gemm2.cu.  The FP64 pipe of the
 // B200 peaks at 37 TFLOP/s; the int8 tensor pipe is two orders of magnitude faster, so even with
 // eight digit planes the exact contraction is several times cheaper than the DMMA kernel.
 //
@@ -213,189 +214,6 @@ __global__ void __launch_bounds__(160, STAGES > 2 ? 1 : 2) i8gemm_kernel(I8Args 
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I8_TMEM_COLS));
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Fused variant for the statistics: the COUNTS are the M side (256 rows per CTA = two M = 128 instructions),
-// the digit planes the N side, interleaved so that the 8 planes of a product column are 8 consecutive
-// accumulator columns of one thread:  n = 8 c + s.  The epilogue recombines them in registers (two int64
-// Horner sums, one rounding) and writes the FP64 statistics directly: no int32 intermediate, no second pass.
-//   out[m][c] = 2^(e_c - 54) sum_s 128^s sum_k cnt[m][k] d_s[k][c],   c < L
-struct I8FusedArgs {
-    const int8_t* Cn; long long ldc; int M;      // counts  [M][ldc]
-    const int8_t* Pl; long long ldp; int L;      // planes  [8 L][ldp], row 8 c + s
-    int K;                                       // multiple of 128
-    const int* expo;                             // [L]
-    double* out; long long ldo;                  // out[m * ldo + c]
-};
-constexpr int F_BM = 256, F_BN = 128;
-constexpr int F_A_BYTES = F_BM * I8_BK, F_B_BYTES = F_BN * I8_BK;     // 32 KB + 16 KB = one 48 KB stage, as above
-constexpr uint32_t F_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-__device__ __forceinline__ void umma_i8_desc(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__global__ void __launch_bounds__(160, 1) i8gemm_fused_kernel(I8FusedArgs p) {
-    extern __shared__ uint8_t smraw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sm + I8_STAGES * I8_STAGE_BYTES);
-    uint64_t* empty = full + I8_STAGES;
-    uint64_t* accum = empty + I8_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * F_BM, n0 = blockIdx.y * F_BN;
-    const int NP = 8 * p.L;                                     // rows of the plane matrix
-    const int nchunks = p.K / I8_BK;
-
-    if (tid == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + s, 128); mbar_init(empty + s, 1); }
-        mbar_init(accum, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(I8_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % I8_STAGES;
-                mbar_wait(full + s, (uint32_t)((c / I8_STAGES) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t a0 = smem_u32(sm + s * I8_STAGE_BYTES), b0 = a0 + F_A_BYTES;
-#pragma unroll
-                for (int k = 0; k < I8_BK / 32; ++k) {
-                    const uint64_t db = umma_desc_sw128(b0 + 32 * k);
-                    const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-                    umma_i8_desc(tmem_d, umma_desc_sw128(a0 + 32 * k), db, F_IDESC, acc);                      // rows 0..127
-                    umma_i8_desc(tmem_d + F_BN, umma_desc_sw128(a0 + 128 * I8_BK + 32 * k), db, F_IDESC, acc);  // rows 128..255
-                }
-                umma_commit(empty + s);
-            }
-            umma_commit(accum);
-        }
-    } else {
-        const int pt = tid - 32;
-        auto issue = [&](int c) {
-            const int s = c % I8_STAGES;
-            uint8_t* sa = sm + s * I8_STAGE_BYTES;
-            uint8_t* sb = sa + F_A_BYTES;
-            const long long k0 = (long long)c * I8_BK;
-#pragma unroll
-            for (int j = 0; j < (F_BM + F_BN) * 8 / 128; ++j) {
-                const int q = pt + 128 * j;
-                const bool isA = q < F_BM * 8;
-                const int qq = isA ? q : q - F_BM * 8;
-                const int row = qq >> 3, c16 = qq & 7;
-                const int grow = (isA ? m0 : n0) + row;
-                const bool ok = grow < (isA ? p.M : NP);
-                const int8_t* src = (isA ? p.Cn + (long long)(ok ? grow : 0) * p.ldc : p.Pl + (long long)(ok ? grow : 0) * p.ldp) + k0 + 16 * c16;
-                uint8_t* dst = (isA ? sa : sb) + (row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4);
-                const int nbytes = ok ? 16 : 0;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(nbytes));
-            }
-            asm volatile("cp.async.commit_group;\n" ::);
-        };
-        auto publish = [&](int c) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_arrive(full + (c % I8_STAGES));
-        };
-        for (int c = 0; c < nchunks; ++c) {
-            if (c >= I8_STAGES) mbar_wait(empty + (c % I8_STAGES), (uint32_t)(((c / I8_STAGES) - 1) & 1));
-            issue(c);
-            if (c >= I8_LAG) {
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(I8_LAG));
-                publish(c - I8_LAG);
-            }
-        }
-        if (nchunks >= 2) { asm volatile("cp.async.wait_group 1;\n" ::); publish(nchunks - 2); }
-        asm volatile("cp.async.wait_group 0;\n" ::);
-        if (nchunks >= 1) publish(nchunks - 1);
-
-        // ===== epilogue: 8 consecutive accumulator columns = the 8 digit planes of one product column
-        mbar_wait(accum, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const int quarter = warp & 3;
-        const int c0 = blockIdx.y * (F_BN / 8);                  // first product column of this CTA
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int row = m0 + h * 128 + quarter * 32 + lane;
-#pragma unroll 1
-            for (int j = 0; j < F_BN / 32; ++j) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * F_BN + j * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                if (row < p.M) {
-                    double r4[4];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const int c = c0 + j * 4 + cc;
-                        long long hi = (int)v[cc * 8 + 7], lo = (int)v[cc * 8 + 3];
-                        hi = hi * 128 + (int)v[cc * 8 + 6]; lo = lo * 128 + (int)v[cc * 8 + 2];
-                        hi = hi * 128 + (int)v[cc * 8 + 5]; lo = lo * 128 + (int)v[cc * 8 + 1];
-                        hi = hi * 128 + (int)v[cc * 8 + 4]; lo = lo * 128 + (int)v[cc * 8 + 0];
-                        // 2^(e_c - 54) as a double: the scaling is an exact multiplication (e_c - 54 is far from the exponent limits
-                        // for any data whose products are representable at all)
-                        const int ex = c < p.L ? p.expo[c] - 54 : 0;
-                        const double sc = __longlong_as_double((long long)(1023 + ex) << 52);
-                        r4[cc] = fma((double)hi, 268435456.0, (double)lo) * sc;
-                    }
-                    double* o = p.out + (long long)row * p.ldo + c0 + j * 4;
-                    if (c0 + j * 4 + 4 <= p.L && (p.ldo & 1) == 0) {
-                        *reinterpret_cast<double2*>(o) = make_double2(r4[0], r4[1]);
-                        *reinterpret_cast<double2*>(o + 2) = make_double2(r4[2], r4[3]);
-                    } else {
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc)
-                            if (c0 + j * 4 + cc < p.L) o[cc] = r4[cc];
-                    }
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(I8_TMEM_COLS));
-    }
-}
-
-// out[m][c] (c < L) for counts [M][ldc] and interleaved planes [8 L][ldp]; returns 1 when the tiles alone would
-// leave most of the GPU idle (the caller then takes the split-K path through the int32 intermediate)
-int launch_i8gemm_fused(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K,
-                        const int* expo, double* out, long long ldo, int min_tiles, cudaStream_t st) {
-    if (K % I8_BK != 0 || (ldc % 16) || (ldp % 16)) return 2;
-    const int mt = (M + F_BM - 1) / F_BM, nt = (8 * L + F_BN - 1) / F_BN;
-    if (mt * nt < min_tiles) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(i8gemm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return 3;
-        attr_set = true;
-    }
-    I8FusedArgs p{Cn, ldc, M, Pl, ldp, L, K, expo, out, ldo};
-    i8gemm_fused_kernel<<<dim3(mt, nt), 160, I8_SMEM, st>>>(p);
-    return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 
 // D[M][ldd] = A[M][lda] . B[N][ldb]^T over k < K (K a multiple of 128); device pointers

@@ -42,13 +42,20 @@ bool plan_stats_zpre(StatsPlan* p, bool trans, bool weights_f64, int mdim_pad, i
 void launch_stats_zpre(const StatsPlan& p, bool trans, const void* wt, const double* sv, const double* F,
                        long long frows, long long ld, int m_valid, double* out, double* Zg, cudaStream_t st);
 
-// ---------------------------------------------------------------- K1 on the integer tensor cores (stats_i8.cu, i8gemm.cu)
+// ---------------------------------------------------------------- K1 on the integer tensor cores (stats_i8.cu, i8gemm.cu, i8gemm2.cu)
+// Fixed-point form of a column of Z: q = rint(Z 2^(54 - e_c)), |q| <= 2^54, in 7 signed base-256 digits d_s in [-128, 127].
+// The digit planes are stored tile-major for the 2-CTA GEMM: a tile = 36 product columns x 7 planes = 252 rows, plane-major.
+constexpr int I8_NPLANES = 7, I8_FIXBITS = 54, I8_COLS_PER_TILE = 36;
+__host__ __device__ inline int i8_plane_row(int c, int s) {
+    return (c / I8_COLS_PER_TILE) * (I8_COLS_PER_TILE * I8_NPLANES) + s * I8_COLS_PER_TILE + (c % I8_COLS_PER_TILE);
+}
+inline int i8_plane_rows(int L) { return ((L + I8_COLS_PER_TILE - 1) / I8_COLS_PER_TILE) * (I8_COLS_PER_TILE * I8_NPLANES); }
 struct StatsI8Sizes { size_t planes_bytes, d_elems, cntT_bytes, bpart_elems; int nsplit_b_row, L; };
 struct StatsI8Buffers {
-    int8_t* planes;                 // [8 L][kdim_pad] signed base-128 digits of Z
+    int8_t* planes;                 // [i8_plane_rows(L)][kdim_pad] signed base-256 digits of Z, tile-major (i8_plane_row)
     unsigned long long* colmax;     // [L] max |Z| per column (bit pattern)
     int* expo;                      // [L] column exponents
-    int32_t* D;                     // [8 L][m_pad] exact digit-plane contractions
+    int32_t* D;                     // [i8_plane_rows(L)][m_pad] exact digit-plane contractions (split-K route only)
     double* bpart;                  // [nsplit][m][K] partial sums of the linear block
     int nsplit_b_row;
     cudaEvent_t ev[3];              // optional timers: before the GEMM, after the GEMM, after the linear block (null: off)

@@ -4,11 +4,11 @@
 //
 // The left operand of the product block is an integer (cnt = number of observed replicates), so every
 // column of Z is written as a fixed-point number against a power-of-two column scale,
-//   Z[k, c] ~ 2^(e_c - 54) q[k, c],   q = round(Z 2^(54 - e_c)),  |q| <= 2^54,   q = sum_{s<8} 128^s d_s,  d_s in [-64, 63],
-// and the eight digit planes are contracted with the counts by ONE exact int8 x int8 -> int32 GEMM on the
-// tcgen05 tensor cores (i8gemm.cu):  D[(s, c), m] = sum_k d_s[k, c] cnt[m, k].  The planes are recombined in
-// integer arithmetic ((D7..D4) and (D3..D0) as two int64 Horner sums, each exactly representable in a
-// double) and rounded once.  The only error is the 2^-55 (relative to the column maximum) rounding of Z
+//   Z[k, c] ~ 2^(e_c - 54) q[k, c],   q = round(Z 2^(54 - e_c)),  |q| <= 2^54,   q = sum_{s<7} 256^s d_s,  d_s in [-128, 127],
+// and the seven digit planes are contracted with the counts by ONE exact int8 x int8 -> int32 GEMM on the
+// tcgen05 tensor cores (i8gemm2.cu: 2-CTA pairs, TMA, recombination in the epilogue; i8gemm.cu: split-K route for
+// shapes with few tiles):  D[(s, c), m] = sum_k d_s[k, c] cnt[m, k].  The planes are recombined in integer arithmetic
+// (two int64 Horner sums re-split into parts that are exactly representable in a double) and rounded once.  The only error is the 2^-55 (relative to the column maximum) rounding of Z
 // itself - below the rounding noise of an FP64 accumulation over the same number of terms - and the result
 // does not depend on the order of summation at all.
 // Replaces the DMMA kernel for the product block (L of the L + K columns: 89 % of the flops at K = 16);
@@ -23,13 +23,13 @@ namespace btf {
 
 int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
                   long long ldd, cudaStream_t st);
-int launch_i8gemm_fused(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K,
-                        const int* expo, double* out, long long ldo, int min_tiles, cudaStream_t st);
+int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K, const int* expo,
+                   double* out, long long ldo, int min_tiles, cudaStream_t st);
 
 namespace {
 
-constexpr int NPLANES = 8;
-constexpr int FIXBITS = 54;
+constexpr int NPLANES = I8_NPLANES;
+constexpr int FIXBITS = I8_FIXBITS;
 
 __device__ __forceinline__ void pair_of(int c, int& k1, int& k2) {
     k1 = (int)((sqrt(8.0 * c + 1.0) - 1.0) * 0.5);
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) zmax_kernel(const double* __restrict__ F,
     }
 }
 
-// digit planes, interleaved: planes[(8 c + s) ldk + r] = d_s of q[r, c].  A block stages 256 rows of F in shared memory;
+// digit planes, tile-major: planes[i8_plane_row(c, s) ldk + r] = d_s of q[r, c] (zero for the padding columns
+// L <= c < n_tiles 36).  A block stages 256 rows of F in shared memory;
 // thread (tx, ty): rows 4 tx .. 4 tx + 3 (one 4-byte store per plane), columns c = ty, ty + 4, ...
 __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__ F, int rows, int rows_pad, int K, int L,
                                                       const unsigned long long* __restrict__ colmax,
@@ -85,30 +86,33 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int r0 = rb + 4 * tx;
     if (r0 >= rows_pad) return;
-    for (int c = ty; c < L; c += 4) {
-        const int k1 = pairs[c] >> 8, k2 = pairs[c] & 0xff;
-        const double mx = __longlong_as_double((long long)colmax[c]);
-        const int e = mx > 0.0 ? ilogb(mx) + 1 : 0;                // max < 2^e
-        if (r0 == 0) expo[c] = e;
+    const int Lslots = (L + I8_COLS_PER_TILE - 1) / I8_COLS_PER_TILE * I8_COLS_PER_TILE;
+    for (int c = ty; c < Lslots; c += 4) {
         unsigned dig[NPLANES];
 #pragma unroll
         for (int s = 0; s < NPLANES; ++s) dig[s] = 0u;
+        if (c < L) {
+            const int k1 = pairs[c] >> 8, k2 = pairs[c] & 0xff;
+            const double mx = __longlong_as_double((long long)colmax[c]);
+            const int e = mx > 0.0 ? ilogb(mx) + 1 : 0;                // max < 2^e
+            if (r0 == 0) expo[c] = e;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double* fr = Fs + (4 * tx + u) * KS;
-            // signed base-128 digits without a carry chain: add 64 at every digit position (C = sum_s 64 128^s
-            // < 2^55.1, so q + C is in (0, 2^56)), read the unsigned 7-bit fields, subtract 64 from each
-            const unsigned long long qq =
-                (unsigned long long)(__double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e)) + 0x0081020408102040ll);
+            for (int u = 0; u < 4; ++u) {
+                const double* fr = Fs + (4 * tx + u) * KS;
+                // signed base-256 digits without a carry chain: add 128 at every digit position (C = sum_{s<7} 128 256^s
+                // < 2^55.1, so q + C is in (0, 2^56)), read the unsigned 8-bit fields, subtract 128 from each
+                const unsigned long long qq =
+                    (unsigned long long)(__double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e)) + 0x0080808080808080ll);
 #pragma unroll
-            for (int s = 0; s < NPLANES; ++s) {
-                const int d = (int)((qq >> (7 * s)) & 127ull) - 64;   // in [-64, 63]
-                dig[s] |= ((unsigned)(d & 0xff)) << (8 * u);
+                for (int s = 0; s < NPLANES; ++s) {
+                    const int d = (int)((qq >> (8 * s)) & 255ull) - 128;   // in [-128, 127]
+                    dig[s] |= ((unsigned)(d & 0xff)) << (8 * u);
+                }
             }
         }
 #pragma unroll
         for (int s = 0; s < NPLANES; ++s)
-            *reinterpret_cast<unsigned*>(planes + ((long long)c * NPLANES + s) * ldk + r0) = dig[s];
+            *reinterpret_cast<unsigned*>(planes + (long long)i8_plane_row(c, s) * ldk + r0) = dig[s];
     }
 }
 
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256, MINB) sf_kernel(const double* __restrict_
     }
 }
 
-// out[m][c] = 2^(e_c - 54) sum_s 128^s D[(8 c + s) ldn + m]  (32 x 32 tiles through shared memory),
+// out[m][c] = 2^(e_c - 54) sum_s 256^s D[i8_plane_row(c, s) ldn + m]  (32 x 32 tiles through shared memory),
 // out[m][L + j] = sum_split bpart[split][m][j]
 __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restrict__ D, long long ldn, const int* __restrict__ expo,
                                                          const double* __restrict__ bpart, int nsplit_b, int m_valid, int L,
@@ -216,13 +220,18 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
             const int c = c0 + cy, m = m0 + tx;
             double v = 0.0;
             if (c < L && m < m_valid) {
-                const int32_t* d = D + (long long)c * NPLANES * ldn + m;
-                const long long pl = ldn;
-                long long hi = d[7 * pl], lo = d[3 * pl];
-                hi = hi * 128 + d[6 * pl]; lo = lo * 128 + d[2 * pl];
-                hi = hi * 128 + d[5 * pl]; lo = lo * 128 + d[1 * pl];
-                hi = hi * 128 + d[4 * pl]; lo = lo * 128 + d[0];
-                v = scalbn(fma((double)hi, 268435456.0, (double)lo), expo[c] - FIXBITS);
+                const int32_t* d = D + m;
+                long long hi = d[(long long)i8_plane_row(c, 6) * ldn];
+                hi = hi * 256 + d[(long long)i8_plane_row(c, 5) * ldn];
+                hi = hi * 256 + d[(long long)i8_plane_row(c, 4) * ldn];
+                long long lo = d[(long long)i8_plane_row(c, 3) * ldn];
+                lo = lo * 256 + d[(long long)i8_plane_row(c, 2) * ldn];
+                lo = lo * 256 + d[(long long)i8_plane_row(c, 1) * ldn];
+                lo = lo * 256 + d[(long long)i8_plane_row(c, 0) * ldn];
+                // H = hi 2^5 + (lo >> 27) and the low 27 bits are exactly representable: one rounding of the exact integer
+                const long long H = hi * 32 + (lo >> 27);
+                const long long l27 = lo & ((1ll << 27) - 1);
+                v = scalbn(fma((double)H, 134217728.0, (double)l27), expo[c] - FIXBITS);
             }
             tile[cy][tx] = v;
         }
@@ -369,15 +378,15 @@ bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col
     if (!(K == 8 || K == 16 || K == 32)) return false;
     if (nreps < 1 || nreps > 127) return false;
     const long long kd = kdim_row > kdim_col ? kdim_row : kdim_col;
-    return kd * nreps * 64 < (1ll << 31);           // the int32 accumulators cannot overflow
+    return kd * nreps * 128 < (1ll << 31);          // the int32 accumulators cannot overflow
 }
 
 void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, int nall_pad, int ploc, StatsI8Sizes* s) {
     const long long L = (long long)K * (K + 1) / 2;
     const long long kd = std::max(nall_pad, Ppad);                          // contraction lengths: rows over p, columns over ALL rows
     const long long nd = std::max<long long>(nloc_pad, (ploc + 255) / 256 * 256);   // output rows: local rows / local columns
-    s->planes_bytes = (size_t)(NPLANES * L * kd);
-    s->d_elems = (size_t)(NPLANES * L * nd);
+    s->planes_bytes = (size_t)i8_plane_rows((int)L) * kd;
+    s->d_elems = (size_t)i8_plane_rows((int)L) * nd;
     s->cntT_bytes = (size_t)std::max(ploc, 1) * nall_pad;
     s->nsplit_b_row = 64;            // upper bound of the split count of the row-variant linear block (buffer size)
     s->bpart_elems = std::max((size_t)s->nsplit_b_row * nloc * K, (size_t)2 * P * K);   // columns: up to two splits per chunk
@@ -407,16 +416,15 @@ void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows
 int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
                      long long d_off, double* out, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
-    const bool force_fused = getenv("BTF_STATS_I8_FUSED") != nullptr && getenv("BTF_STATS_I8_NOFUSED") == nullptr;
-    // (measured on C2: the fused epilogue's FP64 stores are not hidden under the next tile, 0.29 + 0.50 ms against
-    //  0.27 + 0.35 ms + 0.08 ms of recombination, so the int32 route is the default and the fused one is opt-in)
-    if (force_fused) {
-        const int rc = launch_i8gemm_fused(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, kdim_pad, L, kdim_pad,
-                                           w.expo, out, L + K, 0, st);
-        if (rc == 0) return 10;
-        if (rc > 1) return 1;
-    }
-    return launch_i8gemm(w.planes, kdim_pad, NPLANES * L, reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D + d_off,
+    // BTF_I8_GEMM2 = 0: never the 2-CTA kernel; = 1: always (tests); default: when its 256 x 256 tiles fill most CTA pairs
+    static const char* g2 = getenv("BTF_I8_GEMM2");
+    const int min_tiles = g2 ? (g2[0] == '0' ? (1 << 30) : 0) : 48;
+    const int rc = launch_i8gemm2(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, kdim_pad, L, kdim_pad, w.expo, out,
+                                  L + K, min_tiles, st);
+    if (rc == 0) return 10;
+    if (rc > 1) return 1;
+    // few tiles (small tensors, narrow shards): 128 x 256 tiles with split-K and integer atomics through the int32 planes
+    return launch_i8gemm(w.planes, kdim_pad, i8_plane_rows(L), reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D + d_off,
                          m_pad, st) ? 1 : 0;
 }
 
