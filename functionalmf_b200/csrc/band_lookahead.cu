@@ -85,7 +85,13 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     const int Kr = a.K;                                  // true embedding size (<= KB)
     const int L = Kr * (Kr + 1) / 2, nco = L + Kr, kd = Q * Kr, LS = kd + 1;
     const int T = a.T, n = T * Kr;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Role rotation: warp 0 of the role map runs the serial pivot chain of every step.  The hardware puts warp w of a
+    // CTA on scheduler w mod 4, so without rotation the pivot warps of ALL co-resident CTAs share one scheduler (and its
+    // FP64 lanes) while the other three idle between tensor-pipe jobs.  CTAs that share an SM differ in blockIdx / #SMs
+    // (first wave), so rotating the role map by that quotient spreads the pivot chains over the four schedulers.
+    const int lane = threadIdx.x & 31;
+    const int warp = ((int)(threadIdx.x >> 5) + (a.rotate_roles ? (int)(blockIdx.x / a.rotate_roles) : 0)) % NW;
+    const int tid = warp * 32 + lane;
     const int jl = blockIdx.x, jg = a.col_begin + jl;
     const unsigned full = 0xffffffffu;
 

@@ -76,6 +76,9 @@ struct btf_engine {
     double* Yraw = nullptr;      // NB: raw counts [nloc][P][R]
     int nreps = 1;
     bool has_data = false, data_reduced = false;
+    double* staging[2] = {nullptr, nullptr};   // upload staging (kept for the engine's lifetime: no malloc/free per call, no leak on error paths)
+    size_t staging_bytes = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr};
     // NB dispersion
     double* Rdisp = nullptr; int Rn = 1, Rm = 1, Rt = 1; double* nb_work = nullptr;
     double* nb_hist = nullptr; int nb_hist_stride = 0;   // count histograms per R group (integer counts)
@@ -91,7 +94,8 @@ struct btf_engine {
     bool i8_on = false, i8_decided = false;
     StatsI8Buffers i8{};
     unsigned *cnt_rowsum = nullptr, *cnt_colsum = nullptr;   // sum of the counts of every local row / owned (j,t): guard of the fixed-point block
-    int *guard_n = nullptr, *guard_list = nullptr;           // [2] flagged counts (rows, columns), [nloc + Ploc] flagged indices
+    int* guard_n = nullptr;                                  // [2] rows / (j,t) recomputed in FP64 by the last W / V step
+    unsigned char* guard_flags = nullptr;                    // [nloc + Ploc] flags set by the kernels that produce the block
     bool guard_on = true;        // BTF_I8_NO_GUARD=1 switches the element-wise guard off
     uint8_t* cntT = nullptr;     // [Ploc][Nall_pad] counts of this rank's columns over ALL rows (right operand of the column contraction)
     double *mu_mean = nullptr, *mu_m2 = nullptr; long long mu_count = 0; bool mu_track = false;   // posterior moments of Mu
@@ -191,6 +195,8 @@ static bool is_device_ptr(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+void btf_destroy(btf_engine* e);
+
 int btf_create(const btf_config* c, btf_engine** out) {
     if (!c || !out) return set_err(BTF_EINVAL, "null argument");
     if (c->nrows < 1 || c->ncols < 1 || c->ndepth < 2) return set_err(BTF_EINVAL, "bad shape");
@@ -198,6 +204,8 @@ int btf_create(const btf_config* c, btf_engine** out) {
     if (c->tf_order < 0 || c->tf_order > 3) return set_err(BTF_EINVAL, "tf_order must be in [0, 3]");
     if (c->ndepth < c->tf_order + 2) return set_err(BTF_EINVAL, "ndepth must be >= tf_order + 2");
     btf_engine* e = new btf_engine();
+    // every early return below releases what has been created so far (streams, events, device buffers)
+    struct Guard { btf_engine* e; ~Guard() { if (e) btf_destroy(e); } } guard{e};
     e->cfg = *c;
     if (e->cfg.world_size <= 1) {
         e->cfg.world_size = 1; e->cfg.rank = 0;
@@ -210,7 +218,7 @@ int btf_create(const btf_config* c, btf_engine** out) {
     e->nloc = e->cfg.row_end - e->cfg.row_begin;
     e->nloc_pad = round_up(std::max(e->nloc, 1), 128);
     e->Mloc = e->cfg.col_end - e->cfg.col_begin;
-    if (e->nloc < 0 || e->Mloc < 0) { delete e; return set_err(BTF_EINVAL, "bad shard"); }
+    if (e->nloc < 0 || e->Mloc < 0) { return set_err(BTF_EINVAL, "bad shard"); }
     e->Nall_pad = e->cfg.world_size > 1 ? round_up(e->N, 128) : e->nloc_pad;
     e->p0 = e->cfg.col_begin * e->T; e->Ploc = e->Mloc * e->T;
     e->overlap = getenv("BTF_NO_OVERLAP") == nullptr;
@@ -310,9 +318,9 @@ int btf_create(const btf_config* c, btf_engine** out) {
 
     // statistics plans and buffers
     if (!plan_stats(&e->plan_row, e->K, false, pg, e->nloc_pad, e->Ppad, e->nloc, c->stats_splits_row, e->sm_count))
-        { delete e; return set_err(BTF_EINVAL, "no row-statistics plan for K=%d", c->nembeds); }
+        { return set_err(BTF_EINVAL, "no row-statistics plan for K=%d", c->nembeds); }
     if (!plan_stats(&e->plan_col, e->K, true, pg, e->Ppad, e->nloc_pad, e->P, c->stats_splits_col, e->sm_count))
-        { delete e; return set_err(BTF_EINVAL, "no column-statistics plan for K=%d", c->nembeds); }
+        { return set_err(BTF_EINVAL, "no column-statistics plan for K=%d", c->nembeds); }
     CK(dev_alloc(&e->row_stats, e->plan_row.nsplit * e->plan_row.out_elems_per_split));
     CK(dev_alloc(&e->col_stats, e->plan_col.nsplit * e->plan_col.out_elems_per_split));
     {
@@ -338,6 +346,16 @@ int btf_create(const btf_config* c, btf_engine** out) {
     if (e->Rdisp) CK(dev_alloc(&e->snapR, (size_t)e->Rn * e->Rm * e->Rt));
     CK(cudaMallocHost((void**)&e->pinned_scal, 64 * sizeof(double)));
     CK(dev_alloc(&e->diag_retries, std::max(e->Mloc, 1)));
+    // shared-memory needs that grow with the depth (tau2_kernel stages V[j] = T K doubles; the band kernels keep T (q + 1)
+    // + RD doubles of per-column tables): refuse shapes that cannot launch instead of failing inside a sweep
+    {
+        const size_t blk = (size_t)e->Kp * (e->Kp + 4), nblk = (size_t)(e->q + 1) * (e->q + 2) / 2;
+        const size_t need = std::max((size_t)e->T * e->K, (size_t)e->T * (e->q + 1) + e->RD + (nblk + 2) * blk + 1024) * sizeof(double);
+        if (need > (size_t)prop.sharedMemPerBlockOptin)
+            return set_err(BTF_EINVAL, "ndepth = %d needs %zu bytes of shared memory per block, the device offers %zu", e->T, need,
+                           (size_t)prop.sharedMemPerBlockOptin);
+    }
+    guard.e = nullptr;
     *out = e;
     return BTF_OK;
 }
@@ -364,7 +382,7 @@ void btf_destroy(btf_engine* e) {
                     e->snapW, e->snapV, e->snapTau2, e->snapScal, e->snapR, e->diag_retries};
     for (void* p : ptrs) if (p) cudaFree(p);
     {
-        void* i8p[] = {e->i8.planes, e->i8.colmax, e->i8.expo, e->i8.D, e->i8.bpart, e->cntT, e->cnt_rowsum, e->cnt_colsum, e->guard_n, e->guard_list};
+        void* i8p[] = {e->i8.planes, e->i8.colmax, e->i8.expo, e->i8.D, e->i8.bpart, e->cntT, e->cnt_rowsum, e->cnt_colsum, e->guard_n, e->guard_flags};
         for (void* q : i8p) if (q) cudaFree(q);
     }
     for (int i = 0; i < EVAL_SLOTS; ++i) eval_free(e->eval[i]);
@@ -376,6 +394,9 @@ void btf_destroy(btf_engine* e) {
     for (int i = 0; i <= PH_COUNT; ++i) if (e->ph_ev[i]) cudaEventDestroy(e->ph_ev[i]);
     for (int i = 0; i < 6; ++i) if (e->i8_ev[i / 3][i % 3]) cudaEventDestroy(e->i8_ev[i / 3][i % 3]);
     for (int i = 0; i < 2; ++i) {
+        if (e->staging[i]) cudaFree(e->staging[i]);
+        if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
+        if (e->ev_k0[i]) cudaEventDestroy(e->ev_k0[i]);
         if (e->side[i]) cudaStreamDestroy(e->side[i]);
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
     }
@@ -414,31 +435,52 @@ int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int
     if (!e || !Y || nreps < 1 || nreps > 255) return set_err(BTF_EINVAL, "bad arguments (1 <= nreps <= 255)");
     if (e->cfg.likelihood != BTF_GAUSSIAN) return set_err(BTF_ESTATE, "engine is not Gaussian");
     if (row0 < 0 || nrows < 0 || row0 + nrows > e->nloc) return set_err(BTF_EINVAL, "row range outside the shard");
+    if (!reset && e->shard && e->data_reduced)
+        return set_err(BTF_ESTATE, "a sharded engine that has already run holds all-reduced totals: restart the upload with reset = 1");
     CK(cudaSetDevice(e->cfg.device));
     free_graph(e);
     e->nreps = nreps;
     const size_t row_elems = (size_t)e->P * nreps;
     if (reset) CK(cudaMemsetAsync(&e->scal->ss_total, 0, 2 * sizeof(double), e->stream));   // ss_total, n_obs
     const bool on_dev = is_device_ptr(Y);
-    double* staging = nullptr;
     int chunk = nrows;
     if (!on_dev) {
+        // two staging buffers: the copy of piece i + 1 (copy stream) runs under the pre-reduction of piece i
         chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nrows, 1), ((size_t)256 << 20) / (row_elems * 8)));
-        CK(cudaMalloc((void**)&staging, (size_t)chunk * row_elems * sizeof(double)));
+        const size_t need = (size_t)chunk * row_elems * sizeof(double);
+        if (need > e->staging_bytes) {
+            for (int b = 0; b < 2; ++b) { if (e->staging[b]) cudaFree(e->staging[b]); e->staging[b] = nullptr; }
+            e->staging_bytes = 0;
+            for (int b = 0; b < 2; ++b) CK(cudaMalloc((void**)&e->staging[b], need));
+            e->staging_bytes = need;
+        }
+        for (int b = 0; b < 2; ++b) {
+            if (!e->ev_h2d[b]) CK(cudaEventCreateWithFlags(&e->ev_h2d[b], cudaEventDisableTiming));
+            if (!e->ev_k0[b]) CK(cudaEventCreateWithFlags(&e->ev_k0[b], cudaEventDisableTiming));
+        }
+        CK(cudaStreamSynchronize(e->stream));
     }
-    for (int r0 = 0; r0 < nrows; r0 += chunk) {
+    int piece = 0;
+    for (int r0 = 0; r0 < nrows; r0 += chunk, ++piece) {
         int rows = std::min(chunk, nrows - r0);
-        const double* src = on_dev ? Y + (size_t)r0 * row_elems : staging;
-        if (!on_dev) { int rc = upload_rows(e, Y, row_elems, r0, rows, staging); if (rc) return rc; }
+        const int b = piece & 1;
+        const double* src = on_dev ? Y + (size_t)r0 * row_elems : e->staging[b];
+        if (!on_dev) {
+            if (piece >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_k0[b], 0));       // the buffer's previous pre-reduction is done
+            CK(cudaMemcpyAsync(e->staging[b], Y + (size_t)r0 * row_elems, (size_t)rows * row_elems * sizeof(double),
+                               cudaMemcpyHostToDevice, e->copy_stream));
+            CK(cudaEventRecord(e->ev_h2d[b], e->copy_stream));
+            CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[b], 0));
+        }
         int nb = 0;
         const size_t o = (size_t)(row0 + r0) * e->Ppad;
         launch_prereduce_gaussian(src, rows, e->P, nreps, e->cnt + o, e->S + o, e->Ppad, e->partials, &nb, e->stream);
         launch_reduce_add(e->partials, nb, 2, &e->scal->ss_total, e->stream);
         launch_reduce_add(e->partials + 1, nb, 2, &e->scal->n_obs, e->stream);
+        if (!on_dev) CK(cudaEventRecord(e->ev_k0[b], e->stream));
         e->launches += 3;
     }
     CK(cudaStreamSynchronize(e->stream));
-    if (staging) CK(cudaFree(staging));
     CK(cudaGetLastError());
     e->has_data = true; e->data_reduced = false; e->resid_valid = false; e->i8_decided = false;
     return BTF_OK;
@@ -459,9 +501,15 @@ int btf_set_data_binomial(btf_engine* e, const double* Ys, const double* Nt) {
     double *sy = nullptr, *sn = nullptr;
     int chunk = e->nloc;
     if (!on_dev) {
-        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->nloc, ((size_t)128 << 20) / (row_elems * 8)));
-        CK(cudaMalloc((void**)&sy, (size_t)chunk * row_elems * sizeof(double)));
-        CK(cudaMalloc((void**)&sn, (size_t)chunk * row_elems * sizeof(double)));
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(e->nloc, 1), ((size_t)128 << 20) / (row_elems * 8)));
+        const size_t need = (size_t)chunk * row_elems * sizeof(double);
+        if (need > e->staging_bytes) {                 // engine-lifetime staging buffers (freed by btf_destroy)
+            for (int b = 0; b < 2; ++b) { if (e->staging[b]) cudaFree(e->staging[b]); e->staging[b] = nullptr; }
+            e->staging_bytes = 0;
+            for (int b = 0; b < 2; ++b) CK(cudaMalloc((void**)&e->staging[b], need));
+            e->staging_bytes = need;
+        }
+        sy = e->staging[0]; sn = e->staging[1];
     }
     for (int r0 = 0; r0 < e->nloc; r0 += chunk) {
         int rows = std::min(chunk, e->nloc - r0);
@@ -476,8 +524,6 @@ int btf_set_data_binomial(btf_engine* e, const double* Ys, const double* Nt) {
         e->launches += 1;
     }
     CK(cudaStreamSynchronize(e->stream));
-    if (sy) CK(cudaFree(sy));
-    if (sn) CK(cudaFree(sn));
     CK(cudaGetLastError());
     e->has_data = true; e->data_reduced = true; e->i8_decided = false;
     return BTF_OK;
@@ -730,7 +776,9 @@ static int begin_row_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd
     fork_side(e, fork);
     stats_i8_digits(e->i8, e->K, e->V, e->P, e->Ppad, sa);
     if (ev) cudaEventRecord(ev[0], sa);
-    pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, 0, e->row_stats, sa);
+    const I8Guard gr{e->cnt_rowsum, e->guard_flags, e->guard_n, stats_i8_guard_tol()};
+    pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, 0, e->row_stats,
+                                   e->guard_on ? &gr : nullptr, sa);
     if (pd->product != 0 && pd->product != 10) return set_err(BTF_ECUDA, "integer row statistics failed to launch");
     if (ev) cudaEventRecord(ev[1], sa);
     pd->nsplit = stats_i8_linear(e->i8, false, e->K, e->S, e->Ppad, e->V, e->Ppad, e->nloc, e->i8.nsplit_b_row, e->i8.bpart, sb);
@@ -740,11 +788,13 @@ static int begin_row_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd
 }
 static int finish_row_stats_i8(btf_engine* e, bool fork, const I8Pending& pd) {
     join_side(e, fork);
-    stats_i8_combine(e->i8, e->K, e->nloc, e->nloc_pad, 0, pd.product == 10, e->i8.bpart, pd.nsplit, 0, e->nloc, e->row_stats, e->stream);
+    const I8Guard gr{e->cnt_rowsum, e->guard_flags, e->guard_n, stats_i8_guard_tol()};
+    stats_i8_combine(e->i8, e->K, e->nloc, e->nloc_pad, 0, pd.product == 10, e->i8.bpart, pd.nsplit, 0, e->nloc, e->row_stats,
+                     e->guard_on ? &gr : nullptr, e->stream);
     e->launches += 1;
     if (e->guard_on) {
-        stats_i8_guard(e->i8, e->K, e->cnt, e->Ppad, e->V, e->P, e->cnt_rowsum, e->nloc, e->row_stats, e->guard_n, e->guard_list, e->stream);
-        e->launches += 2;
+        stats_i8_fallback(e->K, e->cnt, e->Ppad, e->V, e->P, e->nloc, e->row_stats, gr, e->stream);
+        e->launches += 1;
     }
     return cudaGetLastError() == cudaSuccess ? BTF_OK : set_err(BTF_ECUDA, "integer row statistics failed");
 }
@@ -800,7 +850,9 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
         const int np = ncols * T;
         double* out = e->col_stats + ((size_t)e->p0 + q0) * nco;
         if (np > 0) {
-            product = stats_i8_product(e->i8, e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->Nall_pad, np, ldd, q0, out, sa);
+            const I8Guard gc{e->cnt_colsum + q0, e->guard_flags + std::max(e->nloc, 1) + q0, e->guard_n + 1, stats_i8_guard_tol()};
+            product = stats_i8_product(e->i8, e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->Nall_pad, np, ldd, q0, out,
+                                       e->guard_on ? &gc : nullptr, sa);
             if (product != 0 && product != 10) return set_err(BTF_ECUDA, "integer column statistics failed to launch");
             e->launches++;
             if (!lin_whole) {
@@ -818,14 +870,14 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
         if (lin_whole && !fork) { int rc = linear_whole(); if (rc) return rc; }     // serial mode: one chunk
         if (c == cc.n - 1 && ev) cudaEventRecord(ev[2], sb);
         if (np > 0) {
-            if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, st);
-            else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, st);
+            const I8Guard gc{e->cnt_colsum + q0, e->guard_flags + std::max(e->nloc, 1) + q0, e->guard_n + 1, stats_i8_guard_tol()};
+            const I8Guard* gp = e->guard_on ? &gc : nullptr;
+            if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, gp, st);
+            else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, gp, st);
             e->launches++;
             if (e->guard_on) {
-                // (the flagged counter of the column side accumulates over the chunks of one sweep: reset by the first)
-                stats_i8_guard(e->i8, e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->W, e->N, e->cnt_colsum + q0, np, out,
-                               e->guard_n + 1, e->guard_list + std::max(e->nloc, 1) + q0, st);
-                e->launches += 2;
+                stats_i8_fallback(e->K, e->cntT + (size_t)q0 * e->Nall_pad, e->Nall_pad, e->W, e->N, np, out, gc, st);
+                e->launches += 1;
             }
         }
         if (c == 0) phase_mark(e, PH_BAND_SOLVE);
@@ -863,7 +915,7 @@ static int ensure_i8(btf_engine* e) {
         CK(dev_alloc(&e->cnt_rowsum, (size_t)std::max(e->nloc, 1)));
         CK(dev_alloc(&e->cnt_colsum, (size_t)std::max(e->Ploc, 1)));
         CK(dev_alloc(&e->guard_n, 2));
-        CK(dev_alloc(&e->guard_list, (size_t)std::max(e->nloc, 1) + std::max(e->Ploc, 1)));
+        CK(dev_alloc(&e->guard_flags, (size_t)std::max(e->nloc, 1) + std::max(e->Ploc, 1)));
         e->guard_on = getenv("BTF_I8_NO_GUARD") == nullptr;
         e->i8.nsplit_b_row = z.nsplit_b_row;
     }
@@ -1053,6 +1105,7 @@ static int enqueue_sweep(btf_engine* e) {
         ba.work_L = e->work_L; ba.work_y = e->work_y;
         ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
         ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
+        ba.rotate_roles = getenv("BTF_BAND_NOROT") ? 0 : e->sm_count;
         const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
         ba.diag_band = diag_get(e, "V_band", bn);
         ba.diag_chol = diag_get(e, "V_chol", bn);

@@ -115,6 +115,9 @@ struct G2Args {
     const int* expo;  // [L] column exponents
     double* out;      // out[m * ldo + c]
     long long ldo;
+    // element-wise guard (stats_i8.cu): rows whose diagonal entries cannot be guaranteed to `tol` relative are flagged
+    const unsigned* cntsum; unsigned char* flags; double tol;
+    unsigned long long diag_mask[16];   // per column tile: bit q set when product column nt * 36 + q is a diagonal (k, k)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
@@ -197,6 +200,9 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
             g2_mbar_wait(tfull + acc, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int row = mt * 256 + (int)rank * G2_ROWS + quarter * 32 + lane;
+            const unsigned long long dmask = p.cntsum ? p.diag_mask[nt] : 0ull;
+            const double n_half = (dmask && row < p.M) ? 0.5 * (double)p.cntsum[row] : 0.0;     // error bound = n_m 2^(e_c - 55)
+            bool bad = false;
             const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll 1
             for (int i = 0; i < G2_CPT / 4; ++i) {
@@ -227,6 +233,7 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
                         const int ex = c < p.L ? p.expo[c] - I8_FIXBITS : 0;
                         const double sc = __longlong_as_double((long long)(1023 + ex) << 52);   // 2^(e_c - 54), exact
                         r4[j] = fma((double)H, 134217728.0, (double)l27) * sc;
+                        if ((dmask >> (4 * i + j)) & 1ull) bad = bad || (n_half * sc > p.tol * r4[j]);
                     }
                     double* o = p.out + (long long)row * p.ldo + c0;
                     if (c0 + 4 <= p.L && (p.ldo & 1) == 0 && (c0 & 1) == 0) {
@@ -239,6 +246,7 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
                     }
                 }
             }
+            if (bad) p.flags[row] = 1;
             // this warp has read its lanes of the accumulator: tell the MMA issuer (leader CTA)
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncwarp();
@@ -291,7 +299,7 @@ bool make_map(CUtensorMap* tm, const void* base, long long rows, long long ld, l
 // of 128).  Returns 0 on success, 1 when this kernel does not apply (too few tiles to fill the pairs, alignment, no TMA
 // entry point: the caller takes the split-K route through the int32 planes), > 1 on a launch error.
 int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K, const int* expo,
-                   double* out, long long ldo, int min_tiles, cudaStream_t st) {
+                   double* out, long long ldo, int min_tiles, const I8Guard* guard, cudaStream_t st) {
     if (K % G2_BK != 0 || (ldc % 16) || (ldp % 16) || M < 1 || L < 1) return 1;
     if ((reinterpret_cast<uintptr_t>(Cn) & 15) || (reinterpret_cast<uintptr_t>(Pl) & 15)) return 1;
     const int mt = (M + 255) / 256, nt = (L + G2_CPT - 1) / G2_CPT;
@@ -307,7 +315,13 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
     }
     CUtensorMap tc, td;
     if (!make_map(&tc, Cn, M, ldc, K) || !make_map(&td, Pl, (long long)nt * G2_CPT * G2_NP, ldp, K)) return 1;
-    G2Args p{M, L, K / G2_BK, mt, nt, expo, out, ldo};
+    if (nt > 16) return 1;
+    G2Args p{};
+    p.M = M; p.L = L; p.k_chunks = K / G2_BK; p.m_tiles = mt; p.n_tiles = nt; p.expo = expo; p.out = out; p.ldo = ldo;
+    if (guard) {
+        p.cntsum = guard->cntsum; p.flags = guard->flags; p.tol = guard->tol;
+        for (int k = 0; k * (k + 3) / 2 < L; ++k) { const int c = k * (k + 3) / 2; p.diag_mask[c / G2_CPT] |= 1ull << (c % G2_CPT); }
+    }
     const int pairs = std::min(sms / 2, mt * nt);
     i8gemm2_kernel<<<2 * pairs, G2_THREADS, G2_SMEM, st>>>(tc, td, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;

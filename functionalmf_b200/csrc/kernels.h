@@ -64,20 +64,30 @@ bool stats_i8_supported(int K, int nreps, long long kdim_row, long long kdim_col
 // nall_pad: padded GLOBAL row count (contraction length of the column side), ploc: columns (j,t) owned by this rank
 void stats_i8_sizes(int K, int nloc_pad, int Ppad, int nloc, int P, int nall_pad, int ploc, StatsI8Sizes* s);
 void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, uint8_t* dst, long long ldd, cudaStream_t st);
+// element-wise guard of the fixed-point product block, see below
+struct I8Guard {
+    const unsigned* cntsum;     // [m] sum of the counts of row m (stats_i8_count_rows, once per data set)
+    unsigned char* flags;       // [m] zero except for flagged rows
+    int* nflag;                 // rows recomputed by the last stats_i8_fallback
+    double tol;
+};
 // the four stages of the integer path (engine: tensor-core contraction and HBM-bound linear block on separate streams)
 void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows, int kdim_pad, cudaStream_t st);
 int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
-                     long long d_off, double* out, cudaStream_t st);     // 0: int32 planes in w.D + d_off, 10: fused epilogue wrote out, else error
+                     long long d_off, double* out, const I8Guard* guard, cudaStream_t st);     // 0: int32 planes in w.D + d_off, 10: fused epilogue wrote out, else error
 int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S, long long lds, const double* F,
                     int kdim_pad, int m_valid, int max_split, double* out, cudaStream_t st);     // returns the split count of `out`
 void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, long long d_off, bool product_done,
-                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st);
-// element-wise guard of the fixed-point product block: cntsum[m] = sum_k B[m][k] (once per data set); rows whose
-// diagonal entries cannot be guaranteed to `BTF_I8_GUARD_TOL` (default 1e-12) relative are listed in flagged[0..*nflag)
-// and their product block is recomputed in FP64 (B: counts [m][ldb], F: factor rows [f_rows][K])
+                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out,
+                      const I8Guard* guard, cudaStream_t st);
+// element-wise guard of the fixed-point product block (see stats_i8.cu): the kernels that produce the block flag the rows
+// whose diagonal entries cannot be guaranteed to `tol` relative (2^(e_c - 55) sum_k cnt[m][k] > tol out[m][(k,k)]);
+// stats_i8_fallback recomputes the flagged rows in FP64, clears the flags and counts them in *nflag.
+
+double stats_i8_guard_tol();    // BTF_I8_GUARD_TOL, default 1e-12
 void stats_i8_count_rows(const uint8_t* B, long long ldb, int m_valid, int kdim_pad, unsigned* cntsum, cudaStream_t st);
-void stats_i8_guard(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, const double* F, int f_rows,
-                    const unsigned* cntsum, int m_valid, double* out, int* nflag, int* flagged, cudaStream_t st);
+void stats_i8_fallback(int K, const uint8_t* B, long long ldb, const double* F, int f_rows, int m_valid, double* out,
+                       const I8Guard& g, cudaStream_t st);
 // out[m][L+K] (one split) for count weights: exact product block + FP64 linear block, all stages on one stream
 int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B, long long ldb, const double* S,
                     long long lds, const double* F, int f_rows, int kdim_pad, int m_valid, int m_pad, double* out,
@@ -148,6 +158,7 @@ struct BandSolveArgs {
     double* work_y;        // [ncols_loc][work_y_stride]  y | 1/diag(L)
     size_t work_L_stride, work_y_stride;   // per-column strides (sized for the padded block size)
     int force_psd, attempts; double eps;
+    int rotate_roles;      // look-ahead kernel: > 0 rotates the warp-role map by blockIdx / rotate_roles (= #SMs), 0 = off
     double *diag_band, *diag_chol, *diag_mean; int* diag_retries;
     double* resid_partials;   // [ncols_loc]: sum_t v^T A v - 2 v.b   (nu2 by-product)
 };

@@ -22,28 +22,38 @@ __device__ __forceinline__ double log_phi(double x) {
     return log(0.5 * erfcx(u)) - u * u;
 }
 
-struct PgTilt { double Z, fz, pmass, inv_fz, inv_p, inv_q; };   // + reciprocals reused by every draw of the cell
+// 1/d for a positive, finite, normal d: hardware seed (relative error < 2^-20) and one third-order step
+// y0 (1 + e + e^2), e = 1 - d y0  ->  relative error ~2^-60 plus rounding.  No special-case branch: the IEEE division
+// the compiler emits carries a slow path that is never taken here but costs instruction-cache and issue slots.
+__device__ __forceinline__ double pg_rcp_pos(double d) {
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(y0) : "d"(d));
+    const double e = fma(-d, y0, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(e2, y0, y0);
+}
+
+struct PgTilt { double Z, inv_fz, inv_p, inv_qp; };   // per cell; reused by every draw of the cell
 
 __device__ __forceinline__ PgTilt pg_setup(double z) {
     PgTilt c;
     c.Z = 0.5 * fabs(z);
-    c.fz = PG_PI * PG_PI / 8.0 + 0.5 * c.Z * c.Z;
+    const double fz = PG_PI * PG_PI / 8.0 + 0.5 * c.Z * c.Z;
     const double rt = 1.25;   // sqrt(1 / 0.64)
     double b = rt * (PG_TRUNC * c.Z - 1.0), a = -rt * (PG_TRUNC * c.Z + 1.0);
-    double qdivp;
+    double qdivp;   // q / p: mass of the truncated inverse-Gaussian part over the mass of the exponential tail
     if (c.Z < 12.0) {
-        // fz exp(fz t) [exp(-Z) Phi(b) + exp(Z) Phi(a)] without logarithms (no overflow for |z| < 24)
-        const double ez = exp(-c.Z);
+        // fz exp(fz t) [exp(-Z) Phi(b) + exp(Z) Phi(a)] without logarithms or divisions (no overflow for |z| < 24)
         const double pb = 0.5 * erfc(-b * 0.70710678118654752440), pa = 0.5 * erfc(-a * 0.70710678118654752440);
-        qdivp = 4.0 / PG_PI * c.fz * exp(c.fz * PG_TRUNC) * (ez * pb + pa / ez);
+        const double x0 = fz * PG_TRUNC;
+        qdivp = 4.0 / PG_PI * fz * (exp(x0 - c.Z) * pb + exp(x0 + c.Z) * pa);
     } else {
-        const double x0 = log(c.fz) + c.fz * PG_TRUNC;
+        const double x0 = log(fz) + fz * PG_TRUNC;
         qdivp = 4.0 / PG_PI * (exp(x0 - c.Z + log_phi(b)) + exp(x0 + c.Z + log_phi(a)));
     }
-    c.pmass = 1.0 / (1.0 + qdivp);
-    c.inv_fz = 1.0 / c.fz;
-    c.inv_p = 1.0 + qdivp;                               // 1 / pmass
-    c.inv_q = c.pmass < 1.0 ? 1.0 / (1.0 - c.pmass) : 0.0;
+    c.inv_fz = pg_rcp_pos(fz);
+    c.inv_p = 1.0 + qdivp;                               // 1 / P(exponential tail)
+    c.inv_qp = qdivp > 1e-300 ? pg_rcp_pos(qdivp) : 0.0;  // (u1 / p - 1) / (q / p) is U(0,1) given the inverse-Gaussian branch
     return c;
 }
 
@@ -85,7 +95,7 @@ __device__ __forceinline__ bool leq_exp32(Rng& rng, uint32_t hi, double x) {
 // standard normal Y truncated to Y > 1/sqrt(t) - the Levy law cut at t - so the inner rejection loop (acceptance
 // 0.69 per lane: a warp iterated until its slowest lane got through, ~4 rounds of Philox + log + exp each) is
 // replaced by ONE inversion Y = Phi^-1(U Phi(-1/sqrt(t))): same distribution, no loop, no divergence.
-__device__ double pg_rtigauss(Rng& rng, double Z, double u0, uint32_t a_hi) {
+__device__ double pg_rtigauss(Rng& rng, double Z, double u0, uint32_t a_hi, double& inv_x) {
     const double t = PG_TRUNC;
     bool first = true;
     if (!(Z > 1.0 / t)) {   // mu = 1/Z > t (including Z == 0)
@@ -97,12 +107,14 @@ __device__ double pg_rtigauss(Rng& rng, double Z, double u0, uint32_t a_hi) {
             if (first) { uv = u0; ah = a_hi; first = false; }
             else { const uint4 r = rng.next4(); uv = Rng::to_unit(r.x, r.y); ah = r.z; }
             const double Y = normcdfinv(fmax(uv, 1e-300) * QT);   // < -1.25
-            const double X = 1.0 / (Y * Y);                         // <= t
-            if (leq_exp32(rng, ah, hz2 * X)) return X;
+            const double Y2 = Y * Y;
+            const double X = pg_rcp_pos(Y2);                        // <= t
+            if (leq_exp32(rng, ah, hz2 * X)) { inv_x = Y2; return X; }
         }
+        inv_x = 1.0 / t;
         return t;
     }
-    const double mu = 1.0 / Z;
+    const double mu = pg_rcp_pos(Z);
     for (int it = 0; it < 10000; ++it) {
         double2 nu = rng.normal2();
         double ua = first ? u0 : rng.uniform();
@@ -110,8 +122,9 @@ __device__ double pg_rtigauss(Rng& rng, double Z, double u0, uint32_t a_hi) {
         double Y = nu.x * nu.x;
         double X = mu + 0.5 * mu * mu * Y - 0.5 * mu * sqrt(4.0 * mu * Y + (mu * Y) * (mu * Y));
         if (ua > mu / (mu + X)) X = mu * mu / X;
-        if (X <= t) return X;
+        if (X <= t) { inv_x = 1.0 / X; return X; }
     }
+    inv_x = 1.0 / t;
     return t;
 }
 
@@ -124,10 +137,16 @@ __device__ double pg_one(Rng& rng, const PgTilt& c) {
     for (int it = 0; it < 10000; ++it) {
         const uint4 r = rng.next4();
         const double u1 = Rng::to_unit(r.x, r.y);
-        double X;
-        if (u1 < c.pmass) X = PG_TRUNC - log(u1 * c.inv_p) * c.inv_fz;    // u1 / pmass is U(0,1) given the branch
-        else X = pg_rtigauss(rng, c.Z, (u1 - c.pmass) * c.inv_q, r.z);
-        const double arg = X > PG_TRUNC ? -PG_PI * PG_PI * X : -4.0 / X;
+        double X, arg;
+        const double up = u1 * c.inv_p;                                   // u1 / P(tail): < 1 selects the exponential tail
+        if (up < 1.0) {
+            X = PG_TRUNC - log(up) * c.inv_fz;                            // up is U(0,1) given the branch; X > t
+            arg = -PG_PI * PG_PI * X;
+        } else {
+            double inv_x;
+            X = pg_rtigauss(rng, c.Z, (up - 1.0) * c.inv_qp, r.z, inv_x);  // X <= t, inv_x = 1 / X without a division
+            arg = -4.0 * inv_x;
+        }
         // u2 <= 1 - 3 exp(arg): FP32 screen (the threshold is within 2e-2 of 1), full precision when borderline
         const float thr = 1.0f - 3.0f * __expf((float)arg);
         const float u2f = ((float)r.w + 0.5f) * 2.3283064365386963e-10f;

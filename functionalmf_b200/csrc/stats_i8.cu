@@ -24,7 +24,7 @@ namespace btf {
 int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
                   long long ldd, cudaStream_t st);
 int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K, const int* expo,
-                   double* out, long long ldo, int min_tiles, cudaStream_t st);
+                   double* out, long long ldo, int min_tiles, const I8Guard* guard, cudaStream_t st);
 
 namespace {
 
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) zmax_kernel(const double* __restrict__ F,
     const int nr = min(128, rows - rb);
     for (int e = threadIdx.x; e < nr * K; e += 256) zms[e] = F[(long long)rb * K + e];
     __syncthreads();
-    for (int c = threadIdx.x; c < L; c += 256) {
+    for (int c = threadIdx.x + 256 * blockIdx.y; c < L; c += 256 * gridDim.y) {
         int k1, k2;
         pair_of(c, k1, k2);
         double m0 = 0.0, m1 = 0.0;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
     const int r0 = rb + 4 * tx;
     if (r0 >= rows_pad) return;
     const int Lslots = (L + I8_COLS_PER_TILE - 1) / I8_COLS_PER_TILE * I8_COLS_PER_TILE;
-    for (int c = ty; c < Lslots; c += 4) {
+    for (int c = ty + 4 * blockIdx.y; c < Lslots; c += 4 * gridDim.y) {       // gridDim.y: column groups (few factor rows)
         unsigned dig[NPLANES];
 #pragma unroll
         for (int s = 0; s < NPLANES; ++s) dig[s] = 0u;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256, MINB) sf_kernel(const double* __restrict_
 __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restrict__ D, long long ldn, const int* __restrict__ expo,
                                                          const double* __restrict__ bpart, int nsplit_b, int m_valid, int L,
                                                          int K, double* __restrict__ out, int first_cy,
-                                                         long long bpart_m0, long long bpart_rows) {
+                                                         long long bpart_m0, long long bpart_rows, I8Guard g, int use_guard) {
     __shared__ double tile[32][33];
     const int nco = L + K;
     const int m0 = blockIdx.x * 32, c0 = (blockIdx.y + first_cy) * 32;
@@ -232,6 +232,12 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
                 const long long H = hi * 32 + (lo >> 27);
                 const long long l27 = lo & ((1ll << 27) - 1);
                 v = scalbn(fma((double)H, 134217728.0, (double)l27), expo[c] - FIXBITS);
+                if (use_guard) {
+                    int kk = (int)((sqrtf(8.0f * c + 9.0f) - 3.0f) * 0.5f);             // is c a diagonal column k (k + 3) / 2 ?
+                    while (kk * (kk + 3) / 2 > c) --kk;
+                    while ((kk + 1) * (kk + 4) / 2 <= c) ++kk;
+                    if (kk * (kk + 3) / 2 == c && scalbn((double)g.cntsum[m], expo[c] - (FIXBITS + 1)) > g.tol * v) g.flags[m] = 1;
+                }
             }
             tile[cy][tx] = v;
         }
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
             if (m < m_valid && c < L) out[(long long)m * nco + c] = tile[tx][my];
         }
     } else {
+        if (use_guard && blockIdx.x == 0 && threadIdx.x == 0) *g.nflag = 0;     // (the fallback kernel counts what it recomputes)
         // the linear block: columns L .. L+K-1 (this block row handles all of them for its 32 rows)
         for (int e = threadIdx.x; e < 32 * K; e += 256) {
             const int m = m0 + e / K, j = e % K;
@@ -258,63 +265,63 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int32_t* __restri
 // n_m = sum_k cnt[m][k].  That is 2^-55 relative to the COLUMN maximum: fine normwise, but a row whose observed cells
 // all sit where |Z| is far below the column maximum (structured missingness + badly scaled factors) gets a large
 // RELATIVE error.  The diagonal columns c = (k, k) are sums of non-negative terms, so bound / out[m][(k,k)] is the true
-// relative accuracy of the row's precision matrix; rows where it exceeds `tol` are listed and recomputed in plain FP64.
-__global__ void __launch_bounds__(256) i8_guard_kernel(const double* __restrict__ out, int nco, int m_valid, int K,
-                                                       const int* __restrict__ expo, const unsigned* __restrict__ cntsum,
-                                                       double tol, int* __restrict__ nflag, int* __restrict__ flagged) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= m_valid) return;
-    const double n_m = (double)cntsum[m];
-    bool bad = false;
-    for (int k = 0; k < K; ++k) {
-        const int c = k * (k + 3) / 2;                          // packed index of (k, k)
-        const double bound = scalbn(n_m, expo[c] - (FIXBITS + 1));
-        const double v = out[(long long)m * nco + c];
-        bad = bad || (bound > tol * v);
-    }
-    if (bad) flagged[atomicAdd(nflag, 1)] = m;
-}
-
-// out[m][c] (c < L) = sum_k B[m][k] F[k,k1] F[k,k2] in FP64 for the listed rows: one CTA per row (grid-stride over the
-// list), 128-row slabs of F in shared memory, thread t owns the packed columns t, t + 256, ...
+// relative accuracy of the row's precision matrix; the kernels that produce the block (the GEMM epilogue / the
+// recombination kernel) flag the rows where it exceeds `tol`, and this kernel recomputes those rows in plain FP64:
+// out[m][c] (c < L) = sum_k B[m][k] F[k,k1] F[k,k2].  A CTA scans a contiguous range of flags, then works through the
+// rows it found: 128-row slabs of F in shared memory, thread t owns the packed columns t, t + 256, ...
 template <int MAXC>
 __global__ void __launch_bounds__(256) i8_fallback_kernel(const uint8_t* __restrict__ B, long long ldb, const double* __restrict__ F,
-                                                          int f_rows, int K, int L, const int* __restrict__ nflag,
-                                                          const int* __restrict__ flagged, double* __restrict__ out, int nco) {
+                                                          int f_rows, int K, int L, int m_valid, unsigned char* __restrict__ flags,
+                                                          int* __restrict__ nflag, double* __restrict__ out, int nco) {
     extern __shared__ __align__(16) double fsm[];               // [128][K] + 128 counts
+    __shared__ int list[64];
+    __shared__ int nlist;
     double* Fs = fsm;
     double* Cs = fsm + 128 * K;
-    const int n = *nflag;
+    const int per = (m_valid + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(m_valid, lo + per);
     int k1[MAXC], k2[MAXC];
 #pragma unroll
     for (int q = 0; q < MAXC; ++q) { k1[q] = k2[q] = 0; const int c = threadIdx.x + 256 * q; if (c < L) pair_of(c, k1[q], k2[q]); }
-    for (int it = blockIdx.x; it < n; it += gridDim.x) {
-        const int m = flagged[it];
-        double acc[MAXC][2];
+    for (int base = lo; base < hi; base += 64) {                // (at most 64 rows per round keeps the list in shared memory)
+        if (threadIdx.x == 0) nlist = 0;
+        __syncthreads();
+        if (threadIdx.x < 64 && base + (int)threadIdx.x < hi && flags[base + threadIdx.x]) {
+            list[atomicAdd(&nlist, 1)] = base + threadIdx.x;
+            flags[base + threadIdx.x] = 0;
+        }
+        __syncthreads();
+        const int n = nlist;
+        if (n && threadIdx.x == 0) atomicAdd(nflag, n);
+        for (int it = 0; it < n; ++it) {
+            const int m = list[it];
+            double acc[MAXC][2];
 #pragma unroll
-        for (int q = 0; q < MAXC; ++q) acc[q][0] = acc[q][1] = 0.0;
-        for (int r0 = 0; r0 < f_rows; r0 += 128) {
-            const int nr = min(128, f_rows - r0);
-            __syncthreads();
-            for (int e = threadIdx.x; e < nr * K; e += 256) Fs[e] = F[(long long)r0 * K + e];
-            for (int e = threadIdx.x; e < 128; e += 256) Cs[e] = e < nr ? (double)B[(long long)m * ldb + r0 + e] : 0.0;
-            __syncthreads();
+            for (int q = 0; q < MAXC; ++q) acc[q][0] = acc[q][1] = 0.0;
+            for (int r0 = 0; r0 < f_rows; r0 += 128) {
+                const int nr = min(128, f_rows - r0);
+                __syncthreads();
+                for (int e = threadIdx.x; e < nr * K; e += 256) Fs[e] = F[(long long)r0 * K + e];
+                for (int e = threadIdx.x; e < 128; e += 256) Cs[e] = e < nr ? (double)B[(long long)m * ldb + r0 + e] : 0.0;
+                __syncthreads();
 #pragma unroll
-            for (int q = 0; q < MAXC; ++q) {
-                if (threadIdx.x + 256 * q < L) {
-                    for (int r = 0; r + 1 < nr + 1; r += 2) {
-                        const double c0 = Cs[r], c1 = (r + 1 < nr) ? Cs[r + 1] : 0.0;
-                        if (c0 != 0.0) acc[q][0] = fma(c0, Fs[r * K + k1[q]] * Fs[r * K + k2[q]], acc[q][0]);
-                        if (c1 != 0.0) acc[q][1] = fma(c1, Fs[(r + 1) * K + k1[q]] * Fs[(r + 1) * K + k2[q]], acc[q][1]);
+                for (int q = 0; q < MAXC; ++q) {
+                    if (threadIdx.x + 256 * q < L) {
+                        for (int r = 0; r < nr; r += 2) {
+                            const double c0 = Cs[r], c1 = (r + 1 < nr) ? Cs[r + 1] : 0.0;
+                            if (c0 != 0.0) acc[q][0] = fma(c0, Fs[r * K + k1[q]] * Fs[r * K + k2[q]], acc[q][0]);
+                            if (c1 != 0.0) acc[q][1] = fma(c1, Fs[(r + 1) * K + k1[q]] * Fs[(r + 1) * K + k2[q]], acc[q][1]);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int q = 0; q < MAXC; ++q) {
-            const int c = threadIdx.x + 256 * q;
-            if (c < L) out[(long long)m * nco + c] = acc[q][0] + acc[q][1];
+            for (int q = 0; q < MAXC; ++q) {
+                const int c = threadIdx.x + 256 * q;
+                if (c < L) out[(long long)m * nco + c] = acc[q][0] + acc[q][1];
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -404,26 +411,30 @@ void launch_transpose_u8(const uint8_t* src, long long lds, int rows, int cols, 
 void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows, int kdim_pad, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
     cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
-    zmax_kernel<<<(f_rows + 127) / 128, 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
+    zmax_kernel<<<dim3((f_rows + 127) / 128, (L + 255) / 256), 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
     const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
     static size_t zs_set = 0;
     if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
-    zdigits_kernel<<<(kdim_pad + 255) / 256, 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, (long long)kdim_pad);
+    // few factor rows (the column side: W has N rows): split the product columns over gridDim.y so the launch fills the GPU
+    const int nbx = (kdim_pad + 255) / 256;
+    const int nby = std::max(1, std::min((L + 3) / 4, 592 / nbx));
+    zdigits_kernel<<<dim3(nbx, nby), 256, zs, st>>>(F, f_rows, kdim_pad, K, L, w.colmax, w.expo, w.planes, (long long)kdim_pad);
 }
 
 // 2. exact product block on the tensor cores: D[(8 c + s)][m] = sum_k d_s[k, c] B[m][k], m < m_valid (B = counts, K-major)
 //    returns 0 (int32 planes in w.D), 10 (fused epilogue wrote out[m][c] directly), else an error
 int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, int kdim_pad, int m_valid, int m_pad,
-                     long long d_off, double* out, cudaStream_t st) {
+                     long long d_off, double* out, const I8Guard* guard, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
     // BTF_I8_GEMM2 = 0: never the 2-CTA kernel; = 1: always (tests); default: when its 256 x 256 tiles fill most CTA pairs
     static const char* g2 = getenv("BTF_I8_GEMM2");
     const int min_tiles = g2 ? (g2[0] == '0' ? (1 << 30) : 0) : 48;
     const int rc = launch_i8gemm2(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, kdim_pad, L, kdim_pad, w.expo, out,
-                                  L + K, min_tiles, st);
+                                  L + K, min_tiles, guard, st);
     if (rc == 0) return 10;
     if (rc > 1) return 1;
     // few tiles (small tensors, narrow shards): 128 x 256 tiles with split-K and integer atomics through the int32 planes
+    // (the recombination kernel applies the guard on this route)
     return launch_i8gemm(w.planes, kdim_pad, i8_plane_rows(L), reinterpret_cast<const int8_t*>(B), ldb, m_valid, kdim_pad, w.D + d_off,
                          m_pad, st) ? 1 : 0;
 }
@@ -457,32 +468,35 @@ int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S,
 //    linear-block partials: out[m][0..L) from D, out[m][L..L+K) from bpart[split][bpart_m0 + m][.] (row pitch of a
 //    split = bpart_rows)
 void stats_i8_combine(const StatsI8Buffers& w, int K, int m_valid, int m_pad, long long d_off, bool product_done,
-                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out, cudaStream_t st) {
+                      const double* bpart, int nsplit_b, long long bpart_m0, long long bpart_rows, double* out,
+                      const I8Guard* guard, cudaStream_t st) {
     const int L = K * (K + 1) / 2;
     const int ncy = (L + 31) / 32;
+    const I8Guard g = guard ? *guard : I8Guard{nullptr, nullptr, nullptr, 0.0};
     if (product_done)
         i8_combine_kernel<<<dim3((m_valid + 31) / 32, 1), 256, 0, st>>>(w.D + d_off, m_pad, w.expo, bpart, nsplit_b, m_valid, L, K, out, ncy,
-                                                                       bpart_m0, bpart_rows);
+                                                                       bpart_m0, bpart_rows, g, guard != nullptr);
     else
         i8_combine_kernel<<<dim3((m_valid + 31) / 32, ncy + 1), 256, 0, st>>>(w.D + d_off, m_pad, w.expo, bpart, nsplit_b, m_valid, L, K, out, 0,
-                                                                             bpart_m0, bpart_rows);
+                                                                             bpart_m0, bpart_rows, g, guard != nullptr);
 }
 
-// 5. element-wise guard + FP64 recomputation of the rows it lists (2 small launches; see i8_guard_kernel)
+// 5. FP64 recomputation of the rows flagged by the element-wise guard (see i8_fallback_kernel)
+double stats_i8_guard_tol() {
+    static const double tol = getenv("BTF_I8_GUARD_TOL") ? atof(getenv("BTF_I8_GUARD_TOL")) : 1e-12;
+    return tol;
+}
 void stats_i8_count_rows(const uint8_t* B, long long ldb, int m_valid, int kdim_pad, unsigned* cntsum, cudaStream_t st) {
     if (m_valid > 0) count_rows_kernel<<<(m_valid + 7) / 8, 256, 0, st>>>(B, ldb, m_valid, kdim_pad, cntsum);
 }
-void stats_i8_guard(const StatsI8Buffers& w, int K, const uint8_t* B, long long ldb, const double* F, int f_rows,
-                    const unsigned* cntsum, int m_valid, double* out, int* nflag, int* flagged, cudaStream_t st) {
+void stats_i8_fallback(int K, const uint8_t* B, long long ldb, const double* F, int f_rows, int m_valid, double* out,
+                       const I8Guard& g, cudaStream_t st) {
     if (m_valid <= 0) return;
     const int L = K * (K + 1) / 2, nco = L + K;
-    static const double tol = getenv("BTF_I8_GUARD_TOL") ? atof(getenv("BTF_I8_GUARD_TOL")) : 1e-12;
-    cudaMemsetAsync(nflag, 0, sizeof(int), st);
-    i8_guard_kernel<<<(m_valid + 255) / 256, 256, 0, st>>>(out, nco, m_valid, K, w.expo, cntsum, tol, nflag, flagged);
     const size_t smem = (size_t)(128 * K + 128) * sizeof(double);
-    const int grid = std::min(m_valid, 592);
-    if (L <= 256) i8_fallback_kernel<1><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, nflag, flagged, out, nco);
-    else i8_fallback_kernel<3><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, nflag, flagged, out, nco);
+    const int grid = std::min((m_valid + 63) / 64, 592);
+    if (L <= 256) i8_fallback_kernel<1><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, m_valid, g.flags, g.nflag, out, nco);
+    else i8_fallback_kernel<3><<<grid, 256, smem, st>>>(B, ldb, F, f_rows, K, L, m_valid, g.flags, g.nflag, out, nco);
 }
 
 // All four stages on one stream.
@@ -493,12 +507,12 @@ int launch_stats_i8(const StatsI8Buffers& w, bool trans, int K, const uint8_t* B
                     cudaStream_t st) {
     stats_i8_digits(w, K, F, f_rows, kdim_pad, st);
     if (w.ev[0]) cudaEventRecord(w.ev[0], st);
-    const int pr = stats_i8_product(w, K, B, ldb, kdim_pad, m_valid, m_pad, 0, out, st);
+    const int pr = stats_i8_product(w, K, B, ldb, kdim_pad, m_valid, m_pad, 0, out, nullptr, st);
     if (pr != 0 && pr != 10) return 1;
     if (w.ev[1]) cudaEventRecord(w.ev[1], st);
     const int nsplit = stats_i8_linear(w, trans, K, S, lds, F, kdim_pad, m_valid, trans ? 1 : w.nsplit_b_row, w.bpart, st);
     if (w.ev[2]) cudaEventRecord(w.ev[2], st);
-    stats_i8_combine(w, K, m_valid, m_pad, 0, pr == 10, w.bpart, nsplit, 0, m_valid, out, st);
+    stats_i8_combine(w, K, m_valid, m_pad, 0, pr == 10, w.bpart, nsplit, 0, m_valid, out, nullptr, st);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
