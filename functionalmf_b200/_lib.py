@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbtf_b200.so')
+# BTF_B200_LIB: developer hook for instrumented builds of the same library (tools/band_profile.py)
+LIB_PATH = os.environ.get('BTF_B200_LIB') or os.path.join(_HERE, 'libbtf_b200.so')
 
 BTF_OK, BTF_EINVAL, BTF_ECUDA, BTF_ENOTPD, BTF_ESTATE, BTF_ENCCL = 0, -1, -2, -3, -4, -5
 GAUSSIAN, BINOMIAL, NEGBINOMIAL = 0, 1, 2

@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
             accum += wgt * (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7])));
         }
         double tot = block_sum(accum, red);
-        if (tid == 0) a.resid_partials[jl] = tot;
+        if (threadIdx.x == 0) a.resid_partials[jl] = tot;     // block_sum leaves the total in PHYSICAL thread 0 (roles are rotated)
     }
     LAPROF(5);
 #ifdef BTF_BAND_PROFILE

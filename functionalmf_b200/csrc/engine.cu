@@ -1105,7 +1105,7 @@ static int enqueue_sweep(btf_engine* e) {
         ba.work_L = e->work_L; ba.work_y = e->work_y;
         ba.work_L_stride = e->wL_stride; ba.work_y_stride = e->wy_stride;
         ba.force_psd = c.force_psd; ba.attempts = c.force_psd_attempts; ba.eps = c.force_psd_eps;
-        ba.rotate_roles = getenv("BTF_BAND_NOROT") ? 0 : e->sm_count;
+        ba.rotate_roles = getenv("BTF_BAND_ROT") ? e->sm_count : 0;     // (measured: no gain, off by default)
         const size_t bn = (size_t)e->Mloc * e->n * (e->kd + 1);
         ba.diag_band = diag_get(e, "V_band", bn);
         ba.diag_chol = diag_get(e, "V_chol", bn);

@@ -1,8 +1,12 @@
-import numpy as np, sys
-sys.path.insert(0, '/root/repo')
+"""Band-solve timing over shapes.  With the instrumented library (tools/build_band_profile.sh, BTF_B200_LIB=...) the
+look-ahead kernel also prints per-phase clock64 totals of column 0 (init | B | C1 | C2 (own ...) | backward | resid)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from functionalmf_b200.engine import Engine
 rs = np.random.RandomState(0)
-for (N, M, T, K) in [(4096, 19, 64, 16), (64, 19, 64, 16), (64, 148, 228, 16), (2048, 19, 228, 16), (64, 19, 228, 16), (64, 19, 228, 10)]:
+shapes = [(256, 1024, 64, 16), (256, 148, 64, 16), (256, 256, 128, 32), (256, 148, 128, 32), (64, 19, 228, 10)]
+for (N, M, T, K) in shapes:
     W = rs.normal(size=(N, K)); V = rs.normal(size=(M, T, K)).cumsum(axis=1) * 0.3
     Y = np.einsum('nk,mtk->nmt', W, V)[..., None] + rs.normal(size=(N, M, T, 1))
     eng = Engine(N, M, T, nembeds=K, tf_order=2, seed=1, use_graph=0)
@@ -10,5 +14,6 @@ for (N, M, T, K) in [(4096, 19, 64, 16), (64, 19, 64, 16), (64, 148, 228, 16), (
     eng.sweep(2)
     print('shape', N, M, T, K, flush=True)
     eng.sweep(1); eng.synchronize()
-    print(eng.time_phases(3), flush=True)
+    ph = eng.time_phases(3)
+    print('  band_solve %.3f ms (%.2f us per block step per wave-column)' % (ph['band_solve'], ph['band_solve'] * 1e3 / T), flush=True)
     eng.close()
