@@ -391,25 +391,27 @@ def build_roofline(args, cfg, eng, phases, ms_step, world, device):
                             'ms_per_sweep': lin_ms, 'algorithmic_bytes_per_sweep_per_gpu': byt,
                             'algorithmic_bytes_per_launch': byt / 2.0, 'peak_source': hbm_src,
                             'traffic': _ncu_traffic('sf_kernel', args.workload, world)}
-    # product block (i8gemm_kernel): executed int8 operations and the FP64 flops they replace
+    # product block (i8gemm2_kernel): executed int8 operations and the FP64 flops they replace
     if gemm_ms > 0:
         nloc, nloc_pad = eng.nloc, -(-eng.nloc // 128) * 128
         nall_pad = -(-N // 128) * 128 if world > 1 else nloc_pad
         P, Ppad = M * T, -(-(M * T) // 256) * 256
         ploc = eng.Mloc * T
-        ops = 2.0 * (8 * Lp) * (float(nloc) * Ppad + float(ploc) * nall_pad)
+        ntile = -(-Lp // 36)                       # 36 product columns x 7 digit planes = 252 (+4 idle) accumulator columns per tile
+        r256 = lambda x: -(-x // 256) * 256
+        ops = 2.0 * (256.0 * ntile) * (float(r256(nloc)) * Ppad + float(r256(ploc)) * nall_pad)
         alg = 4.0 * cells * Lp / world
-        fam['i8gemm_kernel'] = {'bound': 'tensor', 'achieved': ops / (gemm_ms * 1e-3) / 1e12, 'peak': i8pk, 'unit': 'TFLOP/s',
-                                'kernel': 'i8gemm_kernel (tcgen05.mma.kind::i8, exact digit-plane contraction of the product block, '
-                                          '2 launches per sweep; achieved = int8 operations AS EXECUTED: 8 digit planes are an '
-                                          'implementation choice, the algorithmic FP64 work is listed beside it)',
-                                'ms_per_sweep': gemm_ms, 'executed_int8_ops_per_sweep_per_gpu': ops,
-                                'algorithmic_fp64_flops_per_sweep_per_gpu': alg,
-                                'algorithmic_fp64_tflops_at_this_time': alg / (gemm_ms * 1e-3) / 1e12, 'fp64_dmma_peak': dmma,
-                                'peak_source': 'btf_i8_peak in this run (resident-operand tcgen05 loop on every SM, %.0f Top/s); '
-                                               'MEASURED_PEAKS.json has no int8 entry (2 x its bf16 burst = %.0f)'
-                                               % (i8pk, 2.0 * (pk.get('bf16_tflops') or 1634.5)),
-                                'traffic': _ncu_traffic('i8gemm_kernel', args.workload, world)}
+        fam['i8gemm2_kernel'] = {'bound': 'tensor', 'achieved': ops / (gemm_ms * 1e-3) / 1e12, 'peak': i8pk, 'unit': 'TFLOP/s',
+                                 'kernel': 'i8gemm2_kernel (tcgen05.mma.cta_group::2.kind::i8 + TMA, exact digit-plane contraction of the '
+                                           'product block, 2 launches per sweep; achieved = int8 operations AS EXECUTED (7 digit planes, '
+                                           '256 x 256 tiles incl. padding): an implementation choice - the algorithmic FP64 work is listed beside it',
+                                 'ms_per_sweep': gemm_ms, 'executed_int8_ops_per_sweep_per_gpu': ops,
+                                 'algorithmic_fp64_flops_per_sweep_per_gpu': alg,
+                                 'algorithmic_fp64_tflops_at_this_time': alg / (gemm_ms * 1e-3) / 1e12, 'fp64_dmma_peak': dmma,
+                                 'peak_source': 'btf_i8_peak in this run (resident-operand tcgen05 loop on every SM, %.0f Top/s); '
+                                                'MEASURED_PEAKS.json has no int8 entry (2 x its bf16 burst = %.0f)'
+                                                % (i8pk, 2.0 * (pk.get('bf16_tflops') or 1634.5)),
+                                 'traffic': _ncu_traffic('i8gemm2_kernel', args.workload, world)}
     # band solve (band_lookahead_kernel): one launch, latency bound; factor traffic + FP64 flops
     if band_ms > 0:
         mloc = eng.Mloc
