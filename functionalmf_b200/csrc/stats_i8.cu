@@ -374,7 +374,10 @@ void launch_sf_cfg(const double* S, long long lds, const double* F, int K, int m
 template <int KB, bool TRANS>
 void launch_sf_t(const double* S, long long lds, const double* F, int K, int m_valid, int m_tiles, int nchunks32,
                  int nsplit, bool resident, int grid, double* out, cudaStream_t st) {
+    // BTF_SF_DEEP=1: chunks of 16 through a 4-stage ring, two CTAs per SM (more, smaller copies in flight)
+    static const bool deep = getenv("BTF_SF_DEEP") != nullptr && getenv("BTF_SF_DEEP")[0] != '0';
     if (resident) launch_sf_cfg<KB, TRANS, 16, 3, 1>(S, lds, F, K, m_valid, m_tiles, nchunks32 * 2, nsplit, grid, out, st);
+    else if (deep) launch_sf_cfg<KB, TRANS, 16, 4, 2>(S, lds, F, K, m_valid, m_tiles, nchunks32 * 2, nsplit, 0, out, st);
     else launch_sf_cfg<KB, TRANS, 32, 2, 2>(S, lds, F, K, m_valid, m_tiles, nchunks32, nsplit, 0, out, st);
 }
 

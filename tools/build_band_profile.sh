@@ -5,8 +5,8 @@ set -e
 HERE="$(cd "$(dirname "$0")/../functionalmf_b200/csrc" && pwd)"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC"
-mkdir -p "$HERE/_obj"
-$NVCC $FLAGS -DBTF_BAND_PROFILE -c "$HERE/band_lookahead.cu" -o "$HERE/_obj/band_lookahead_prof.o"
+mkdir -p "$HERE/_obj" "$HERE/_obj_prof"
+$NVCC $FLAGS -DBTF_BAND_PROFILE -c "$HERE/band_lookahead.cu" -o "$HERE/_obj_prof/band_lookahead_prof.o"
 objs=$(ls "$HERE"/_obj/*.o | grep -v band_lookahead)
-$NVCC -shared -o "$HERE/../libbtf_b200_prof.so" $objs "$HERE/_obj/band_lookahead_prof.o" -ldl
+$NVCC -shared -o "$HERE/../libbtf_b200_prof.so" $objs "$HERE/_obj_prof/band_lookahead_prof.o" -ldl
 echo built "$HERE/../libbtf_b200_prof.so"
