@@ -59,10 +59,7 @@ struct LaGeom {
     static constexpr int NW = KB > 16 ? 8 : 4;             // warp 0: potrf; warps 1..: workers
     static constexpr int NT = 32 * NW;
     static constexpr int NWK = NW - 1, NWT = 32 * NWK;
-    // KB <= 16: 7 CTAs per SM (72 registers, <= 32.3 KB of shared memory) = 1036 resident columns: the 1024 columns of
-    // the headline configuration are ONE wave instead of 592 + 432 (the kernel is a dependency chain: throughput comes
-    // from co-resident columns)
-    static constexpr int MINB = KB > 16 ? 2 : 7;      // KB = 32: 2 CTAs per SM (128 registers, 114 KB)
+    static constexpr int MINB = KB > 16 ? 1 : 4;
     static constexpr int COLE = (Q + 1) * KK;              // global block column: Linv_t | L_1t .. L_Qt
     static constexpr int BWD = COLE + KB;                  // + y_t : one backward stage
     static constexpr int NST = 3;                          // backward stages: the block column of step t-2 is in flight during step t
@@ -71,14 +68,9 @@ struct LaGeom {
     static constexpr int PF = (KB * (KB + 1) / 2 + NWT - 1) / NWT;   // prefetched statistics per worker thread
     __host__ __device__ static constexpr int base(int d) { return d * (Q + 1) - d * (d - 1) / 2; }
     __device__ static __forceinline__ int slot(int a, int d) { return base(d) + a % (Q + 1 - d); }
-    // forward-only buffers (right-hand-side window, y_t, pivot column, pivots) and backward-only buffers (solution window,
-    // right-hand sides, normals) share one region; the reduction scratch of the epilogue overlays it too
-    static constexpr int FWD = (Q + 1) * KB + KB + 64 + 32;
-    static constexpr int BWDB = 2 * (Q + 1) * KB + 2 * KB + 2 * KB;
-    static constexpr int SHR = (FWD > BWDB ? FWD : BWDB) > 48 ? (FWD > BWDB ? FWD : BWDB) : 48;
     static size_t smem_doubles(int T, int RD) {
-        (void)T;                                                    // the per-depth prior band lives in the global workspace
-        return (size_t)(WREG > RD ? WREG : RD) + 2 * BLK + SHR;    // the RD prior precisions only live until the band is built
+        return (size_t)WREG + 2 * BLK + (Q + 1) * KB + KB + 2 * (Q + 1) * KB + 2 * KB + 2 * KB + (size_t)T * (Q + 1) +
+               RD + 48 + 96 + (KB * (KB + 1) / 2 + 3) / 4;
     }
 };
 
@@ -103,21 +95,19 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     const int jl = blockIdx.x, jg = a.col_begin + jl;
     const unsigned full = 0xffffffffu;
 
-    double* Wb = sm;                                   // [NBLK][BLK] window  (backward: NST stages of BWD; at start: the RD prior precisions)
-    double* Li = Wb + (G::WREG > a.RD ? G::WREG : a.RD);   // [2][BLK]   inverse of the diagonal factor (padded rows)
-    double* shr = Li + 2 * BLK;                        // forward buffers | backward buffers | reduction scratch (one region)
-    double* bw = shr;                                  // [Q+1][KB]  right-hand-side window                (forward)
-    double* ycur = bw + (Q + 1) * KB;                  // [KB]                                             (forward)
-    double* colb = ycur + KB;                          // [2][32] pivot column of the potrf warp           (forward)
-    double* dbuf = colb + 64;                          // [32]    pivots d_j, then 1/sqrt(d_j)             (forward)
-    double* xw = shr;                                  // [2][Q+1][KB] backward solution window            (backward)
-    double* rb = xw + 2 * (Q + 1) * KB;                // [2][KB]    backward right-hand sides             (backward)
-    double* zb = rb + 2 * KB;                          // [2][KB]    normals of the current / next step    (backward)
-    double* red = shr;                                 // [48]       block reduction                       (epilogue)
-    double* linv = Wb;                                 // [RD]       prior precisions, dead once the band is built
-    // prior band P[t][d] = (Delta^T diag(.) Delta)[t + d, t] of this column: global workspace behind y (read once per
-    // entering block row, prefetched into registers next to the statistics)
-    double* Pband = a.work_y + (size_t)blockIdx.x * a.work_y_stride + (size_t)a.T * KB;   // [T][Q+1]
+    double* Wb = sm;                                   // [NBLK][BLK] window  (backward: NST stages of BWD)
+    double* Li = Wb + G::WREG;                         // [2][BLK]   inverse of the diagonal factor (padded rows)
+    double* bw = Li + 2 * BLK;                         // [Q+1][KB]  right-hand-side window
+    double* ycur = bw + (Q + 1) * KB;                  // [KB]
+    double* xw = ycur + KB;                            // [2][Q+1][KB] backward solution window
+    double* rb = xw + 2 * (Q + 1) * KB;                // [2][KB]    backward right-hand sides
+    double* zb = rb + 2 * KB;                          // [2][KB]    normals of the current / next backward step
+    double* Pband = zb + 2 * KB;                       // [T][Q+1]
+    double* linv = Pband + (size_t)T * (Q + 1);        // [RD]
+    double* red = linv + a.RD;                         // [40]
+    double* colb = red + 48;                           // [2][32] pivot column of the potrf warp
+    double* dbuf = colb + 64;                          // [32]    pivots d_j, then 1/sqrt(d_j)
+    unsigned short* pairtab = reinterpret_cast<unsigned short*>(dbuf + 32);   // [L] packed index -> (i << 8 | c)
     __shared__ int fail_flag;
 
     const double scale = a.homoskedastic ? 1.0 / a.scal->nu2 : 1.0;
@@ -128,13 +118,10 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         linv[r] = pv;
     }
     if (tid == 0) fail_flag = 0;
-    // packed lower-triangle index e -> (row i, column c), e = i (i + 1) / 2 + c
-    auto unpack = [](int e, int& i, int& c) {
-        i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while (i * (i + 1) / 2 > e) --i;
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        c = e - i * (i + 1) / 2;
-    };
+    for (int e = tid; e < Kr * Kr; e += NT) {
+        const int i = e / Kr, c = e % Kr;
+        if (c <= i) pairtab[tri(i, c)] = (unsigned short)((i << 8) | c);
+    }
     __syncthreads();
     for (int e = tid; e < T * (Q + 1); e += NT) {
         double s = 0.0;
@@ -163,12 +150,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     bool failed = false;
 
     // everything of block row `arow` except the statistics: prior band, padding, off-diagonal blocks
-    // pb[d] = P[arow - d][d], d = 0..Q: the prior-band entries of block row `arow`
-    auto load_pb = [&](int arow, double* pb) {
-#pragma unroll
-        for (int d = 0; d <= Q; ++d) pb[d] = arow - d >= 0 ? Pband[(arow - d) * (Q + 1) + d] : 0.0;
-    };
-    auto init_rest = [&](int arow, int t0, int nthreads, const double* pb) {
+    auto init_rest = [&](int arow, int t0, int nthreads) {
         double* D = Wb + G::slot(arow, 0) * BLK;
         for (int e = t0; e < (KB - Kr) * KB; e += nthreads) {          // padding rows Kr..KB-1: identity
             const int i = Kr + e / KB, c = e % KB;
@@ -178,7 +160,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         for (int d = 1; d <= Q; ++d) {                                 // (arow, arow - d) = P[arow][arow-d] * I
             if (arow - d >= 0) {
                 double* B = Wb + G::slot(arow, d) * BLK;
-                const double pv = pb[d];
+                const double pv = Pband[(arow - d) * (Q + 1) + d];
                 for (int e = t0; e < KB * KB; e += nthreads) {
                     const int i = e / KB, c = e % KB;
                     B[i * KS + c] = (i == c && i < Kr) ? pv : 0.0;
@@ -190,11 +172,10 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
         }
     };
     // one packed lower-triangle entry of the diagonal block
-    auto put_diag = [&](int arow, int e, double sv, double pb0) {
-        int i, c;
-        unpack(e, i, c);
+    auto put_diag = [&](int arow, int e, double sv) {
+        const int i = pairtab[e] >> 8, c = pairtab[e] & 0xff;
         double v = sv * scale;
-        if (c == i) v += pb0 + jitter;
+        if (c == i) v += Pband[arow * (Q + 1)] + jitter;
         if (a.diag_band) a.diag_band[((size_t)jl * n + arow * Kr + i) * LS + kd - (i - c)] = v;
         Wb[G::slot(arow, 0) * BLK + i * KS + c] = v;
     };
@@ -206,12 +187,10 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
     // assemble a whole block row with direct loads (initial window)
     auto init_row = [&](int arow, int t0, int nthreads) {
         const double* sb = have_stats ? stats0 + (size_t)arow * nco : nullptr;
-        double pb[Q + 1];
-        load_pb(arow, pb);
-        for (int e = t0; e < L; e += nthreads) put_diag(arow, e, have_stats ? stat_sum(sb + e) : 0.0, pb[0]);
+        for (int e = t0; e < L; e += nthreads) put_diag(arow, e, have_stats ? stat_sum(sb + e) : 0.0);
         for (int e = t0; e < KB; e += nthreads)
             bw[(arow % (Q + 1)) * KB + e] = (have_stats && e < Kr) ? stat_sum(sb + L + e) * scale : 0.0;
-        init_rest(arow, t0, nthreads, pb);
+        init_rest(arow, t0, nthreads);
     };
 
     // warp 0: Cholesky of the diagonal block of step t in registers (lane = row) and its inverse into
@@ -448,10 +427,6 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
                 const bool enter = arow < T;
                 // (a) statistics of the entering block row: loads in flight during the tensor-pipe work
                 double pf[PF][2], pfb[2] = {0.0, 0.0};
-                double pbr[Q + 1];
-#pragma unroll
-                for (int d = 0; d <= Q; ++d) pbr[d] = 0.0;
-                if (enter) load_pb(arow, pbr);
 #pragma unroll
                 for (int i = 0; i < PF; ++i) pf[i][0] = pf[i][1] = 0.0;
                 if (enter && have_stats) {
@@ -558,10 +533,10 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
 #pragma unroll
                     for (int i = 0; i < PF; ++i) {
                         const int e = wt + i * NWT;
-                        if (e < L) put_diag(arow, e, pf[i][0] + pf[i][1], pbr[0]);
+                        if (e < L) put_diag(arow, e, pf[i][0] + pf[i][1]);
                     }
                     if (wt < KB) bw[(arow % (Q + 1)) * KB + wt] = (pfb[0] + pfb[1]) * scale;
-                    init_rest(arow, wt, NWT, pbr);
+                    init_rest(arow, wt, NWT);
                 }
             }
 #ifdef BTF_BAND_PROFILE
@@ -679,7 +654,7 @@ __global__ void __launch_bounds__(LaGeom<KB, Q>::NT, LaGeom<KB, Q>::MINB) band_l
             int k1 = 0, k2 = 0;
             double wgt = -2.0;
             if (c < L) {
-                unpack(c, k1, k2);
+                k1 = pairtab[c] >> 8; k2 = pairtab[c] & 0xff;
                 wgt = k1 == k2 ? 1.0 : 2.0;
             } else {
                 k1 = c - L;

@@ -349,9 +349,9 @@ int btf_create(const btf_config* c, btf_engine** out) {
     // shared-memory needs that grow with the depth (tau2_kernel stages V[j] = T K doubles; the band kernels keep T (q + 1)
     // + RD doubles of per-column tables): refuse shapes that cannot launch instead of failing inside a sweep
     {
-        // tau2_kernel stages V[j] (T K doubles); the look-ahead band kernel overlays the RD prior precisions on its window
+        // tau2_kernel stages V[j] (T K doubles); the band kernels keep T (q + 1) + RD doubles of per-column tables next to their window
         const size_t blk = (size_t)e->Kp * (e->Kp + 4), nblk = (size_t)(e->q + 1) * (e->q + 2) / 2;
-        const size_t need = std::max((size_t)e->T * e->K, std::max((size_t)e->RD, nblk * blk) + 2 * blk + 1024) * sizeof(double);
+        const size_t need = std::max((size_t)e->T * e->K, (size_t)e->T * (e->q + 1) + e->RD + (nblk + 2) * blk + 1024) * sizeof(double);
         if (need > (size_t)prop.sharedMemPerBlockOptin)
             return set_err(BTF_EINVAL, "ndepth = %d needs %zu bytes of shared memory per block, the device offers %zu", e->T, need,
                            (size_t)prop.sharedMemPerBlockOptin);
