@@ -1,8 +1,9 @@
 // K3 (blocked, look-ahead): batched block-banded FP64 Cholesky + MVN draw for the V columns.
 //
-// Same mathematics and the same window / workspace conventions as band_blocked_kernel
-// (band_blocked.cu; replaces sample_mvn_from_precision + CHOLMOD, fast_mvn.py:33-74, and the
-// kron / SpGEMM assembly of factor.py:396-408), reorganised around the one chain that cannot be
+// Replaces sample_mvn_from_precision + CHOLMOD (fast_mvn.py:33-74) and the kron / SpGEMM assembly of
+// factor.py:396-408: right-looking block-banded Cholesky with KB x KB blocks (block half-bandwidth Q = order + 1)
+// in a shift-free circular shared-memory window, the per-column statistics prefetched from global memory, the
+// factor spilled by block columns for the backward solve.  Organised around the one chain that cannot be
 // parallelised - the KB sequential pivots of every diagonal block:
 //   * the diagonal block of step t+1 is factorised by warp 0 WHILE the other warps finish the
 //     trailing update of step t, spill block column t and assemble the entering block row

@@ -7,7 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v"
 mkdir -p "$HERE/_obj"
 pids=()
-for f in engine stats_kernels stats_zpre solve_kernels band_blocked band_lookahead hyper_kernels pg_kernels eval_kernels i8gemm i8gemm2 stats_i8 nccl_shard fp64_peak; do
+for f in engine stats_kernels stats_zpre solve_kernels band_lookahead hyper_kernels pg_kernels eval_kernels i8gemm i8gemm2 stats_i8 nccl_shard fp64_peak; do
   ( $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" > "$HERE/_obj/$f.log" 2>&1 || { cat "$HERE/_obj/$f.log"; exit 1; } ) &
   pids+=($!)
 done

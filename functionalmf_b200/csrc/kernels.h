@@ -163,8 +163,6 @@ struct BandSolveArgs {
     double* resid_partials;   // [ncols_loc]: sum_t v^T A v - 2 v.b   (nu2 by-product)
 };
 void launch_band_solve(const BandSolveArgs& a, cudaStream_t st);
-// blocked (DMMA) variant for K in {8,16,32}; returns false when the shape has no instantiation
-bool launch_band_solve_blocked(const BandSolveArgs& a, cudaStream_t st);
 // look-ahead variant (band_lookahead.cu): potrf of step t+1 overlapped with the trailing update of step t
 bool launch_band_solve_lookahead(const BandSolveArgs& a, cudaStream_t st);
 

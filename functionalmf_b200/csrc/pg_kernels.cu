@@ -7,6 +7,7 @@
 // moment-matched normal approximation (the rule of the hybrid sampler the
 // reference's third-party dependency implements).  All randomness is Philox,
 // keyed by (seed, sweep, global cell index).
+#include <cstdlib>
 #include "kernels.h"
 
 namespace btf {
@@ -210,8 +211,8 @@ __device__ double pg_draw(Rng& rng, double b, double z) {
 }
 
 // ---------------------------------------------------------------- omega ~ PG(ntr, w.v)
-template <int KMAX>
-__global__ void __launch_bounds__(256) pg_draw_kernel(PgArgs a) {
+template <int KMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) pg_draw_kernel(PgArgs a) {
     __shared__ double ws[32 * KMAX];
     const int K = a.K;
     const int p = blockIdx.x * 256 + threadIdx.x;
@@ -324,9 +325,18 @@ void launch_pg_draw(const PgArgs& a, cudaStream_t st) {
         return;
     }
     dim3 grid((a.P + 255) / 256, (a.nloc + 31) / 32);
-    if (a.K <= 8) pg_draw_kernel<8><<<grid, 256, 0, st>>>(a);
-    else if (a.K <= 16) pg_draw_kernel<16><<<grid, 256, 0, st>>>(a);
-    else pg_draw_kernel<32><<<grid, 256, 0, st>>>(a);
+    // BTF_PG_OCC=3: 80 registers / three CTAs per SM instead of 126 / two (the sampler is a chain of dependent FP64 operations:
+    // more resident warps hide more of its latency, at the price of a few spilled values)
+    static const bool occ3 = getenv("BTF_PG_OCC") != nullptr && getenv("BTF_PG_OCC")[0] == '3';
+    if (occ3) {
+        if (a.K <= 8) pg_draw_kernel<8, 3><<<grid, 256, 0, st>>>(a);
+        else if (a.K <= 16) pg_draw_kernel<16, 3><<<grid, 256, 0, st>>>(a);
+        else pg_draw_kernel<32, 2><<<grid, 256, 0, st>>>(a);
+        return;
+    }
+    if (a.K <= 8) pg_draw_kernel<8, 2><<<grid, 256, 0, st>>>(a);
+    else if (a.K <= 16) pg_draw_kernel<16, 2><<<grid, 256, 0, st>>>(a);
+    else pg_draw_kernel<32, 2><<<grid, 256, 0, st>>>(a);
 }
 
 __global__ void pg_sample_kernel(const double* b, const double* z, double* out, long long n, uint64_t seed,

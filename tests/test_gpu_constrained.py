@@ -76,3 +76,37 @@ def test_nonconjugate_ess_chain_runs_and_improves_fit():
     assert np.all(res['W'][:, np.triu_indices(K, k=1)[0], np.triu_indices(K, k=1)[1]] == 0)
     assert m.logprob(Y) > ll0 + 10          # slice sampling never decreases below the slice; the fit improves
     assert np.all(np.isfinite(res['Tau2'])) and np.all(res['sigma2'] > 0)
+
+
+@pytest.mark.parametrize('case', [0, 1, 2])
+def test_ess_prior_draws_match_reference_pack_path(case):
+    """the ellipse of NonconjugateBayesianTensorFiltering is spanned by ONE prior draw per update.  The
+    reference packs W / V into a vector, builds the packed prior precision (`_pack_W`, `_pack_V`, factor.py:155-194) and
+    calls `sample_mvn_from_precision` (fast_mvn.py:33-47); the engine draws the same priors for all free W entries / all
+    columns of V in one batched step (K2 / K3 with zero statistics).  Same standard normals in, same draws out: fixtures
+    of oracle/make_golden_ess_prior.py (unmodified reference, recorded noise), including nrows < nembeds."""
+    from functionalmf_b200 import NonconjugateBayesianTensorFiltering
+    from functionalmf_b200 import _lib as L
+    z = np.load(os.path.join(GOLDEN, 'ess_prior.npz'))
+    p = 'c%d_' % case
+    N, M, T, K, order = [int(x) for x in z[p + 'cfg']]
+    m = NonconjugateBayesianTensorFiltering(N, M, T, lambda W, V, d: 0.0, nembeds=K, tf_order=order,
+                                            sigma2_init=float(z[p + 'sigma2']), lam2_init=float(z[p + 'lam2']),
+                                            Tau2_init=z[p + 'Tau2'], seed=9)
+    m._sync_ep()
+    free = m._free_mask()
+    # W: x = sqrt(sigma2) z on the free entries, structural zeros elsewhere
+    m._engine_step(L.SAMPLE_W, 'z_W', z[p + 'z_W'])
+    Wp = m._engine.get('W')
+    assert np.all(Wp[~free] == 0)
+    assert np.max(np.abs(Wp[free] - z[p + 'prior_W'][free])) <= 1e-12 * np.max(np.abs(z[p + 'prior_W']))
+    # V: x_j = chol(Delta^T diag(1 / (lam2 tau2_j)) Delta (x) I_K)^-T z_j; the reference factorises the same matrix in
+    # k-major order, so the draws agree to kappa * eps
+    m._engine_step(L.SAMPLE_V, 'z_V', z[p + 'z_V'])
+    Vp = m._engine.get('V')
+    Delta = np.asarray(m.Delta.todense())
+    for j in range(M):
+        P = Delta.T @ ((1.0 / (float(z[p + 'lam2']) * z[p + 'Tau2'][j]))[:, None] * Delta)
+        tol = max(1e-10, 50 * np.linalg.cond(P) * np.finfo(float).eps)
+        err = np.max(np.abs(Vp[j] - z[p + 'prior_V'][j])) / np.max(np.abs(z[p + 'prior_V'][j]))
+        assert err < tol, (j, err, tol)
