@@ -4,6 +4,7 @@
 #include "kernels.h"
 #include "nccl_shard.h"
 
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -610,6 +611,15 @@ int btf_set_state(btf_engine* e, const char* name, const double* host, size_t n)
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
     std::string nm(name);
+    if (nm == "sweep") {
+        // the sweep counter is a Philox counter word: restoring it (with the seed and the state arrays) resumes a chain
+        // on exactly the random stream it would have continued with
+        if (n != 1 || !(host[0] >= 0.0) || host[0] > 9007199254740992.0) return set_err(BTF_EINVAL, "sweep: one non-negative integer below 2^53");
+        const unsigned long long v = (unsigned long long)host[0];
+        CK(cudaMemcpy(&e->scal->sweep, &v, sizeof(v), cudaMemcpyHostToDevice));
+        e->resid_valid = false;
+        return BTF_OK;
+    }
     if ((nm == "omega" && e->omega) || (nm == "Ntrials" && e->ntr)) {
         if (n != (size_t)e->nloc * e->P) return set_err(BTF_EINVAL, "%s: expected %zu values", name, (size_t)e->nloc * e->P);
         return copy_pitched(e, nm == "omega" ? e->omega : e->ntr, const_cast<double*>(host), false);
@@ -619,6 +629,9 @@ int btf_set_state(btf_engine* e, const char* name, const double* host, size_t n)
     if (n != r.n) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, r.n, n);
     CK(cudaMemcpy(r.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
     if (nm == "W" || nm == "V") e->resid_valid = false;
+    // restoring a checkpoint: the residual sum that belongs to the (W, V) just set, so that the next nu2 step uses the same
+    // number the interrupted chain would have used (set it AFTER W and V)
+    if (nm == "resid" && e->cfg.likelihood == BTF_GAUSSIAN && e->has_data) e->resid_valid = true;
     return BTF_OK;
 }
 
@@ -627,6 +640,13 @@ int btf_get_state(btf_engine* e, const char* name, double* host, size_t n) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
     std::string nm(name);
+    if (nm == "sweep") {
+        if (n != 1) return set_err(BTF_EINVAL, "sweep: 1 value");
+        unsigned long long v = 0;
+        CK(cudaMemcpy(&v, &e->scal->sweep, sizeof(v), cudaMemcpyDeviceToHost));
+        host[0] = (double)v;
+        return BTF_OK;
+    }
     if (nm == "Delta") {
         if (n != e->delta.size()) return set_err(BTF_EINVAL, "Delta: expected %zu values", e->delta.size());
         memcpy(host, e->delta.data(), n * sizeof(double));
@@ -748,8 +768,17 @@ int btf_get_diag(btf_engine* e, const char* name, double* host, size_t n) {
 }
 
 // ------------------------------------------------------------------ the sweep
+// Phase boundaries: CUDA events for btf_time_phases, and NVTX ranges (BTF_NVTX=1) so that a timeline tool shows
+// nu2 / sigma2 / tau2 / lam2 / row_stats / row_solve / col_stats / band_solve / comm around the launches of a sweep.
+static const char* const kPhaseNames[] = {"btf:nu2_or_pg", "btf:sigma2", "btf:tau2", "btf:lam2", "btf:row_stats", "btf:row_solve",
+                                          "btf:col_stats", "btf:band_solve", "btf:comm"};
 static inline void phase_mark(btf_engine* e, int idx) {
     if (e->time_phases) cudaEventRecord(e->ph_ev[idx], e->stream);
+    static const bool nvtx = getenv("BTF_NVTX") != nullptr;
+    if (nvtx) {
+        if (idx > 0) nvtxRangePop();
+        if (idx < PH_COUNT) nvtxRangePushA(kPhaseNames[idx]);
+    }
 }
 
 // ---- K1 on the integer tensor cores, staged over the engine's streams (stats_i8.cu).

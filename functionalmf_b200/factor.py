@@ -309,6 +309,47 @@ class BayesianTensorFiltering(_BayesianModel):
         self._engine.sweep(1)
         self._end()
 
+    # ---- checkpoint / resume (the reference has none; a 12 h chain on 8 GPUs wants one)
+    _CKPT_ARRAYS = ('W', 'V', 'Tau2', 'Tau2_a', 'Tau2_b', 'Tau2_c')
+
+    def save_checkpoint(self, path):
+        """Everything a chain needs to continue bit for bit: the state arrays and scalars, the Philox seed and the sweep
+        counter (a Philox counter word), plus R for the negative-binomial model.  One ``.npz`` file; on a sharded model
+        every rank holds the same state, so rank 0's file is enough."""
+        eng = self._engine
+        out = {k: eng.get(k) for k in self._CKPT_ARRAYS}
+        for k in self._scalar_names():
+            out[k] = np.array(eng.get_scalar(k))
+        out['sweep'] = np.array(eng.get_scalar('sweep'))
+        out['resid'] = np.array(eng.get_scalar('resid'))      # Gaussian: residual sum of the saved (W, V), input of the next nu2 step
+        out['seed'] = np.array(int(eng.cfg.seed), dtype=np.uint64)
+        if getattr(eng.cfg, 'likelihood', 0) == L.NEGBINOMIAL:
+            out['R'] = eng.get('R')
+        np.savez(path, **out)
+
+    def load_checkpoint(self, path):
+        """Restore a state written by ``save_checkpoint`` into a model built with the same shape and ``seed``; the next
+        sweep is the one the saved chain would have run."""
+        z = np.load(path)
+        eng = self._engine
+        if int(z['seed']) != int(eng.cfg.seed):
+            raise ValueError('checkpoint was written with seed %d, this model has seed %d: pass seed=%d to the constructor'
+                             % (int(z['seed']), int(eng.cfg.seed), int(z['seed'])))
+        for k in self._CKPT_ARRAYS:
+            if z[k].shape != eng.state_shape(k):
+                raise ValueError('checkpoint %s has shape %r, the model expects %r' % (k, z[k].shape, eng.state_shape(k)))
+            eng.set(k, z[k])
+        for k in self._scalar_names():
+            eng.set(k, [float(z[k])])
+        if 'R' in z.files:
+            eng.set('R', z['R'])
+        eng.set('sweep', [float(z['sweep'])])
+        if self._data_key is not None and 'resid' in z.files:
+            eng.set('resid', [float(z['resid'])])              # after W and V (which invalidate it); needs the data on the device
+        self._pull_state()
+        if 'R' in z.files and hasattr(self, 'R'):
+            self.R = eng.get('R')
+
     # ---- results
     def _alloc_results(self, nsamples):
         host = pinned_empty if self._pinned_results else (lambda s: np.empty(s, dtype=np.float64))
