@@ -62,7 +62,8 @@ struct btf_engine {
     int sm_count;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};   // forked inside a sweep: tensor-core product block | HBM-bound linear block
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_digits = nullptr;
+    bool sf_after_digits = false;   // BTF_SF_AFTER_DIGITS=1: the linear block starts with the GEMM (after the digit kernels), co-residency experiment
     cudaEvent_t ev_chunk[2][16] = {{nullptr}};   // per column chunk of the V step: product block done | linear block done
     int col_chunks = 1;          // BTF_COL_CHUNKS: the V step can run as a pipeline over column chunks (off by default: see DESIGN.md)
     bool overlap = true;         // BTF_NO_OVERLAP=1: everything on one stream (A/B runs)
@@ -237,10 +238,15 @@ int btf_create(const btf_config* c, btf_engine** out) {
     }
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&e->side[i], cudaStreamNonBlocking, lo)); }
+        // side[0] (tensor-core product block) above side[1] (linear block): when both have CTAs pending, the GEMM's persistent
+        // CTA pairs are placed first and the linear block fills what is left of every SM
+        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+          CK(cudaStreamCreateWithPriority(&e->side[i], cudaStreamNonBlocking, i == 0 ? std::min(lo, hi + 1) : lo)); }
         CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_digits, cudaEventDisableTiming));
+    e->sf_after_digits = getenv("BTF_SF_AFTER_DIGITS") != nullptr;
     for (int i = 0; i < 32; ++i) CK(cudaEventCreateWithFlags(&e->ev_chunk[i / 16][i % 16], cudaEventDisableTiming));
     if (const char* cc = getenv("BTF_COL_CHUNKS")) e->col_chunks = std::min(16, std::max(1, atoi(cc)));
     CK(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
@@ -403,6 +409,7 @@ void btf_destroy(btf_engine* e) {
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
     }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_digits) cudaEventDestroy(e->ev_digits);
     for (int i = 0; i < 32; ++i) if (e->ev_chunk[i / 16][i % 16]) cudaEventDestroy(e->ev_chunk[i / 16][i % 16]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -805,6 +812,7 @@ static int begin_row_stats_i8(btf_engine* e, bool fork, int timer, I8Pending* pd
     cudaEvent_t* ev = (e->time_phases && timer >= 0) ? e->i8_ev[timer] : nullptr;
     fork_side(e, fork);
     stats_i8_digits(e->i8, e->K, e->V, e->P, e->Ppad, sa);
+    if (fork && e->sf_after_digits) { cudaEventRecord(e->ev_digits, sa); cudaStreamWaitEvent(sb, e->ev_digits, 0); }
     if (ev) cudaEventRecord(ev[0], sa);
     const I8Guard gr{e->cnt_rowsum, e->guard_flags, e->guard_n, stats_i8_guard_tol()};
     pd->product = stats_i8_product(e->i8, e->K, e->cnt, e->Ppad, e->Ppad, e->nloc, e->nloc_pad, 0, e->row_stats,
@@ -860,6 +868,7 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
     fork_side(e, fork);
     if (ev) cudaEventRecord(ev[0], sa);
     if (e->Ploc > 0) { stats_i8_digits(e->i8, e->K, e->W, e->N, e->Nall_pad, sa); e->launches += 2; }
+    if (fork && e->sf_after_digits) { cudaEventRecord(e->ev_digits, sa); cudaStreamWaitEvent(sb, e->ev_digits, 0); }
     if (ev) cudaEventRecord(ev[0], sa);
     // linear block: sharded engines need the partial sums of ALL columns before the exchange -> one launch
     // (on the side stream when forked; in the serial mode it is issued after the product block, see below)

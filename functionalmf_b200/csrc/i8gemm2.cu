@@ -31,10 +31,10 @@ namespace {
 
 constexpr int G2_ROWS = 128;                 // count rows / digit rows per CTA and stage
 constexpr int G2_BK = 128;                   // bytes of K per stage
-constexpr int G2_STAGES = 6;
+constexpr int G2_MAX_STAGES = 6;                          // 4 stages (130 KB) leave room for one CTA of the linear-block kernel per SM
 constexpr int G2_TILE_BYTES = G2_ROWS * G2_BK;            // 16 KB
 constexpr int G2_STAGE_BYTES = 2 * G2_TILE_BYTES;         // counts + digits
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int g2_smem(int stages) { return stages * G2_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/; }
 constexpr int G2_TMEM_COLS = 512;            // two accumulator stages of 256 columns
 constexpr int G2_THREADS = 192;              // warp 0: TMA, warp 1: MMA + tensor-memory allocation, warps 2-5: epilogue
 constexpr int G2_CPT = I8_COLS_PER_TILE;     // 36 product columns per tile
@@ -120,6 +120,7 @@ struct G2Args {
     unsigned long long diag_mask[16];   // per column tile: bit q set when product column nt * 36 + q is a diagonal (k, k)
 };
 
+template <int G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ CUtensorMap tm_dig, G2Args p) {
     extern __shared__ uint8_t smraw[];
@@ -310,9 +311,14 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(i8gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) { cudaGetLastError(); return 1; }
+        if (cudaFuncSetAttribute(i8gemm2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem(6)) != cudaSuccess ||
+            cudaFuncSetAttribute(i8gemm2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem(4)) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
         attr_ok = true;
     }
+    static const bool four = getenv("BTF_I8_G2_STAGES") != nullptr && getenv("BTF_I8_G2_STAGES")[0] == '4';
     CUtensorMap tc, td;
     if (!make_map(&tc, Cn, M, ldc, K) || !make_map(&td, Pl, (long long)nt * G2_CPT * G2_NP, ldp, K)) return 1;
     if (nt > 16) return 1;
@@ -323,7 +329,8 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
         for (int k = 0; k * (k + 3) / 2 < L; ++k) { const int c = k * (k + 3) / 2; p.diag_mask[c / G2_CPT] |= 1ull << (c % G2_CPT); }
     }
     const int pairs = std::min(sms / 2, mt * nt);
-    i8gemm2_kernel<<<2 * pairs, G2_THREADS, G2_SMEM, st>>>(tc, td, p);
+    if (four) i8gemm2_kernel<4><<<2 * pairs, G2_THREADS, g2_smem(4), st>>>(tc, td, p);
+    else i8gemm2_kernel<6><<<2 * pairs, G2_THREADS, g2_smem(6), st>>>(tc, td, p);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

@@ -224,18 +224,24 @@ __global__ void __launch_bounds__(256, MINB) pg_draw_kernel(PgArgs a) {
     __syncthreads();
     if (p >= a.P) return;
     const unsigned long long sweep = a.scal->sweep;
-    for (int r = 0; r < 32; ++r) {
+    // the observed flag and the trial count of row r + 1 are loaded while row r is sampled (the loads were 10 % of the
+    // stall samples: every row started with a dependent global load)
+    const int nrow = min(32, a.nloc - i0);
+    unsigned char ob_n = 0; double nt_n = 0.0;
+    if (nrow > 0) { const size_t o0 = (size_t)i0 * a.ld + p; ob_n = a.obs[o0]; nt_n = a.ntr[o0]; }
+    for (int r = 0; r < nrow; ++r) {
         const int il = i0 + r;
-        if (il >= a.nloc) break;
         const size_t o = (size_t)il * a.ld + p;
+        const unsigned char ob = ob_n; const double nt = nt_n;
+        if (r + 1 < nrow) { ob_n = a.obs[o + a.ld]; nt_n = a.ntr[o + a.ld]; }
         double om = 0.0;
-        if (a.obs[o]) {
+        if (ob) {
             double psi = 0.0;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k)
                 if (k < K) psi += ws[r * K + k] * v[k];
             Rng rng(a.seed, STREAM_PG, sweep, (uint64_t)(a.row_begin + il) * a.P + p);
-            om = pg_draw(rng, a.ntr[o], psi);
+            om = pg_draw(rng, nt, psi);
         }
         a.omega[o] = om;
     }
@@ -325,9 +331,9 @@ void launch_pg_draw(const PgArgs& a, cudaStream_t st) {
         return;
     }
     dim3 grid((a.P + 255) / 256, (a.nloc + 31) / 32);
-    // BTF_PG_OCC=3: 80 registers / three CTAs per SM instead of 126 / two (the sampler is a chain of dependent FP64 operations:
-    // more resident warps hide more of its latency, at the price of a few spilled values)
-    static const bool occ3 = getenv("BTF_PG_OCC") != nullptr && getenv("BTF_PG_OCC")[0] == '3';
+    // 80 registers / three CTAs per SM instead of 126 / two (the sampler is a chain of dependent FP64 operations: more
+    // resident warps hide more of its latency, at the price of a few spilled values): 11.4 -> 10.4 ms at C3; BTF_PG_OCC=2 for the old build
+    static const bool occ3 = !(getenv("BTF_PG_OCC") != nullptr && getenv("BTF_PG_OCC")[0] == '2');
     if (occ3) {
         if (a.K <= 8) pg_draw_kernel<8, 3><<<grid, 256, 0, st>>>(a);
         else if (a.K <= 16) pg_draw_kernel<16, 3><<<grid, 256, 0, st>>>(a);
