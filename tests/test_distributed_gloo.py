@@ -95,3 +95,82 @@ def test_two_rank_seed_agreement_and_state_check(tmp_path):
     b = np.load(tmp_path / 's1.npy')
     assert a[0] == 1000 and b[0] == 1000          # rank 0's seed on both ranks
     assert a[1] == 1.0 and b[1] == 1.0            # the mismatch is reported on every rank
+
+
+def _colshard_worker(rank, world, port, out_dir):
+    """CPU emulation of the round-2 V-step decomposition with the same index arithmetic as
+    nccl_shard.cu: ring exchange of the transposed count tiles (world rounds of one send + one receive), product block of
+    the OWN columns over ALL rows, linear block as partial sums over the LOCAL rows reduced to the owner."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from functionalmf_b200.distributed import Shard
+    N, M, T, K = 300, 7, 5, 3
+    rs = np.random.RandomState(9)
+    cnt = rs.randint(0, 4, size=(N, M * T)).astype(np.uint8)
+    S = rs.normal(size=(N, M * T)) * (cnt > 0)
+    W = rs.normal(size=(N, K))
+    shards = [Shard(r, world, N, M, row_align=128) for r in range(world)]
+    me = shards[rank]
+    r0, r1 = me.rows
+    c0, c1 = me.cols
+    pad = lambda n: -(-n // 128) * 128
+    nall_pad = pad(N)
+    # local transposed counts [P][nloc_pad]
+    srcT = np.zeros((M * T, pad(max(r1 - r0, 1))), dtype=np.uint8)
+    srcT[:, :r1 - r0] = cnt[r0:r1].T
+    ploc = (c1 - c0) * T
+    cntT = np.zeros((max(ploc, 1), nall_pad), dtype=np.uint8)
+    for r in range(world):                      # nccl_exchange_counts
+        to, frm = (rank + r) % world, (rank - r + world) % world
+        f0, f1 = shards[frm].rows
+        if r == 0:
+            block = srcT[c0 * T:c1 * T]
+        else:
+            t0, t1 = shards[to].cols
+            send = torch.from_numpy(np.ascontiguousarray(srcT[t0 * T:t1 * T]))
+            recv = torch.zeros((ploc, pad(max(f1 - f0, 1))), dtype=torch.uint8)
+            reqs = []
+            if send.numel():
+                reqs.append(dist.isend(send, to))
+            if recv.numel():
+                reqs.append(dist.irecv(recv, frm))
+            for q in reqs:
+                q.wait()
+            block = recv.numpy()
+        if ploc and f1 > f0:
+            cntT[:ploc, f0:f1] = block[:, :f1 - f0]
+    # product block of the own columns over all rows; linear block: partial sums over local rows, summed across ranks
+    il = np.tril_indices(K)
+    Z = W[:, il[0]] * W[:, il[1]]
+    prod = cntT[:ploc, :N].astype(float) @ Z
+    part = torch.from_numpy(S[r0:r1].T @ W[r0:r1])          # [P][K] for ALL columns
+    dist.all_reduce(part)                                      # (the engine reduce-scatters; every rank keeps its block)
+    lin = part.numpy()[c0 * T:c1 * T]
+    np.save(os.path.join(out_dir, 'c%d.npy' % rank), np.concatenate([[c0, c1], prod.ravel(), lin.ravel()]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_column_sharded_statistics(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_colshard_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    N, M, T, K = 300, 7, 5, 3
+    rs = np.random.RandomState(9)
+    cnt = rs.randint(0, 4, size=(N, M * T)).astype(np.uint8)
+    S = rs.normal(size=(N, M * T)) * (cnt > 0)
+    W = rs.normal(size=(N, K))
+    il = np.tril_indices(K)
+    want_prod = cnt.T.astype(float) @ (W[:, il[0]] * W[:, il[1]])
+    want_lin = S.T @ W
+    seen = 0
+    for r in range(world):
+        a = np.load(tmp_path / ('c%d.npy' % r))
+        c0, c1 = int(a[0]), int(a[1])
+        ploc, L = (c1 - c0) * T, len(il[0])
+        prod = a[2:2 + ploc * L].reshape(ploc, L)
+        lin = a[2 + ploc * L:].reshape(ploc, K)
+        assert np.allclose(prod, want_prod[c0 * T:c1 * T], rtol=1e-12, atol=1e-12)
+        assert np.allclose(lin, want_lin[c0 * T:c1 * T], rtol=1e-12, atol=1e-12)
+        seen += c1 - c0
+    assert seen == M
