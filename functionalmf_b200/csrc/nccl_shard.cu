@@ -254,6 +254,54 @@ int nccl_exchange_counts(NcclShard* s, const uint8_t* srcT, long long src_ld, in
     return 0;
 }
 
+// Column-sharded copy of an FP64 row-sharded matrix: dst[i][p - p0] = src_rank(i)[i - rb][p] for ALL rows i and this rank's
+// columns p in [p0, p1).  src: this rank's rows [nloc][src_ld]; dst: [N_pad][dst_ld]; tmp: >= max_rows * max_ploc doubles for
+// the packed send block and as many for the receive block.  Same ring of `world` rounds as the count exchange.
+int nccl_exchange_rows_f64(NcclShard* s, const double* src, long long src_ld, int T, double* dst, long long dst_ld,
+                           double* tmp_send, double* tmp_recv, cudaStream_t st) {
+    const int me = s->rank, W = s->world;
+    const size_t ploc = (size_t)(s->ce[me] - s->cb[me]) * T;
+    const size_t nloc = (size_t)(s->re[me] - s->rb[me]);
+    for (int r = 0; r < W; ++r) {
+        const int to = (me + r) % W, from = (me - r + W) % W;
+        const size_t to_w = (size_t)(s->ce[to] - s->cb[to]) * T;          // columns the receiver owns
+        const size_t from_rows = (size_t)(s->re[from] - s->rb[from]);
+        if (r == 0) {
+            if (ploc && nloc &&
+                cudaMemcpy2DAsync(dst + (size_t)s->rb[me] * dst_ld, (size_t)dst_ld * 8, src + (size_t)s->cb[me] * T, (size_t)src_ld * 8,
+                                  ploc * 8, nloc, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+                snprintf(g_nccl_err, sizeof(g_nccl_err), "strided copy of a data block failed");
+                return -1;
+            }
+            continue;
+        }
+        // pack my rows x the receiver's columns, exchange, unpack the sender's rows x my columns
+        if (to_w && nloc &&
+            cudaMemcpy2DAsync(tmp_send, to_w * 8, src + (size_t)s->cb[to] * T, (size_t)src_ld * 8, to_w * 8, nloc,
+                              cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            snprintf(g_nccl_err, sizeof(g_nccl_err), "packing a data block failed");
+            return -1;
+        }
+        NC(g_api.GroupStart());
+        if (to_w * nloc) NC(g_api.Send(tmp_send, to_w * nloc, ncclFloat64, to, s->comm, st));
+        if (ploc * from_rows) NC(g_api.Recv(tmp_recv, ploc * from_rows, ncclFloat64, from, s->comm, st));
+        NC(g_api.GroupEnd());
+        if (ploc && from_rows &&
+            cudaMemcpy2DAsync(dst + (size_t)s->rb[from] * dst_ld, (size_t)dst_ld * 8, tmp_recv, ploc * 8, ploc * 8, from_rows,
+                              cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            snprintf(g_nccl_err, sizeof(g_nccl_err), "unpacking a data block failed");
+            return -1;
+        }
+    }
+    return 0;
+}
+
+int nccl_shard_max_cols(const NcclShard* s) {
+    int m = 0;
+    for (int r = 0; r < s->world; ++r) m = std::max(m, s->ce[r] - s->cb[r]);
+    return m;
+}
+
 int nccl_allreduce_sum(NcclShard* s, double* p, int n, cudaStream_t st) {
     NC(g_api.AllReduce(p, p, (size_t)n, ncclFloat64, ncclSum, s->comm, st));
     return 0;

@@ -32,6 +32,10 @@ int nccl_reduce_scatter_cols(NcclShard* s, double* buf, size_t per_col_elems, cu
 // in-place all-gather of the column blocks of `narr` arrays [M][RD] (the Tau2 chain)
 int nccl_allgather_tau(NcclShard* s, double* const* arrays, int narr, int RD, cudaStream_t st);
 int nccl_shard_max_rows(const NcclShard* s);
+int nccl_shard_max_cols(const NcclShard* s);
+// column-sharded copy of a row-sharded FP64 matrix (see nccl_shard.cu)
+int nccl_exchange_rows_f64(NcclShard* s, const double* src, long long src_ld, int T, double* dst, long long dst_ld,
+                           double* tmp_send, double* tmp_recv, cudaStream_t st);
 // column-sharded copy of the uint8 counts (see nccl_shard.cu)
 int nccl_exchange_counts(NcclShard* s, const uint8_t* srcT, long long src_ld, int T, uint8_t* dst, long long dst_ld,
                          uint8_t* tmp, cudaStream_t st);

@@ -96,13 +96,19 @@ __global__ void __launch_bounds__(256) zdigits_kernel(const double* __restrict__
             const double mx = __longlong_as_double((long long)colmax[c]);
             const int e = mx > 0.0 ? ilogb(mx) + 1 : 0;                // max < 2^e
             if (r0 == 0) expo[c] = e;
+            // 2^(54 - e) as a double: the scaling is then ONE exact multiplication per entry (scalbn is a library call of ~25
+            // instructions); exponents outside the normal range (column maxima below 2^-968 or above 2^1000) keep scalbn
+            const int se = FIXBITS - e;
+            const bool fast = se > -1000 && se < 1000;
+            const double sc = fast ? __longlong_as_double((long long)(1023 + se) << 52) : 1.0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const double* fr = Fs + (4 * tx + u) * KS;
+                const double z = fr[k1] * fr[k2];
                 // signed base-256 digits without a carry chain: add 128 at every digit position (C = sum_{s<7} 128 256^s
                 // < 2^55.1, so q + C is in (0, 2^56)), read the unsigned 8-bit fields, subtract 128 from each
                 const unsigned long long qq =
-                    (unsigned long long)(__double2ll_rn(scalbn(fr[k1] * fr[k2], FIXBITS - e)) + 0x0080808080808080ll);
+                    (unsigned long long)(__double2ll_rn(fast ? z * sc : scalbn(z, se)) + 0x0080808080808080ll);
 #pragma unroll
                 for (int s = 0; s < NPLANES; ++s) {
                     const int d = (int)((qq >> (8 * s)) & 255ull) - 128;   // in [-128, 127]
