@@ -877,9 +877,13 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
     // (on the side stream when forked; in the serial mode it is issued after the product block, see below)
     const bool lin_whole = e->shard != nullptr || cc.n == 1;
     const bool scol = e->shard != nullptr && e->Scol != nullptr;     // own columns over all rows: nothing to exchange
+    int whole_split = 1;
     auto linear_whole = [&]() -> int {
         if (scol) {
-            if (e->Ploc > 0) { stats_i8_linear(e->i8, true, e->K, e->Scol, e->Ploc_pad, e->W, e->Nall_pad, e->Ploc, 1, e->i8.bpart, sb); e->launches++; }
+            // (few row tiles per rank: split the contraction so that the launch still fills the GPU; the partials fit in the
+            //  2 P K doubles of the buffer because P_loc <= P / world ... and at least P / 2 for two ranks)
+            const int max_split = std::max(1, std::min(8, (int)((2ll * e->P) / std::max(e->Ploc, 1))));
+            if (e->Ploc > 0) { whole_split = stats_i8_linear(e->i8, true, e->K, e->Scol, e->Ploc_pad, e->W, e->Nall_pad, e->Ploc, max_split, e->i8.bpart, sb); e->launches++; }
         } else if (e->nloc > 0) {
             stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, Wloc, e->nloc_pad, e->P, 1, e->i8.bpart, sb); e->launches++;
         } else {
@@ -920,7 +924,7 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
         if (np > 0) {
             const I8Guard gc{e->cnt_colsum + q0, e->guard_flags + std::max(e->nloc, 1) + q0, e->guard_n + 1, stats_i8_guard_tol()};
             const I8Guard* gp = e->guard_on ? &gc : nullptr;
-            if (lin_whole && scol) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, q0, e->Ploc, out, gp, st);
+            if (lin_whole && scol) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, whole_split, q0, e->Ploc, out, gp, st);
             else if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, gp, st);
             else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, gp, st);
             e->launches++;
