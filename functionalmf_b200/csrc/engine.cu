@@ -189,8 +189,23 @@ static std::vector<double> build_delta(int T, int order, int* RD_out) {
 
 template <typename Tp>
 static cudaError_t dev_alloc(Tp** p, size_t n, bool zero = true) {
+    // cudaMemset of device memory returns before the fill has run, and the fill is ordered on the LEGACY stream, which
+    // the engine's non-blocking streams do not wait for: without the synchronize a kernel enqueued right after the
+    // allocation can have its output zeroed underneath it (seen as a half-zeroed column count matrix at C2 sizes).
     cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(Tp));
-    if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(Tp));
+    if (e == cudaSuccess && zero) {
+        e = cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(Tp), cudaStreamLegacy);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    }
+    return e;
+}
+
+// Blocking host-to-device copy that has LANDED when it returns: cudaMemcpy from pageable memory may return once the bytes
+// are staged, the transfer itself being ordered on the legacy stream only - which the engine's non-blocking streams do
+// not wait for.
+static cudaError_t h2d(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
 }
 
@@ -286,13 +301,13 @@ int btf_create(const btf_config* c, btf_engine** out) {
         }
     CK(dev_alloc(&e->d_start, RD)); CK(dev_alloc(&e->d_width, RD)); CK(dev_alloc(&e->d_coef, hc.size()));
     CK(dev_alloc(&e->pm_ptr, pp.size())); CK(dev_alloc(&e->pm_row, pr.size())); CK(dev_alloc(&e->pm_coef, pc.size()));
-    CK(cudaMemcpy(e->d_start, hs.data(), RD * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_width, hw.data(), RD * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_coef, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->pm_ptr, pp.data(), pp.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(h2d(e->d_start, hs.data(), RD * sizeof(int)));
+    CK(h2d(e->d_width, hw.data(), RD * sizeof(int)));
+    CK(h2d(e->d_coef, hc.data(), hc.size() * sizeof(double)));
+    CK(h2d(e->pm_ptr, pp.data(), pp.size() * sizeof(int)));
     if (!pr.empty()) {
-        CK(cudaMemcpy(e->pm_row, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(e->pm_coef, pc.data(), pc.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(h2d(e->pm_row, pr.data(), pr.size() * sizeof(int)));
+        CK(h2d(e->pm_coef, pc.data(), pc.size() * sizeof(double)));
     }
 
     // state (W and V padded with zero rows so the statistics tiles may over-read)
@@ -305,12 +320,12 @@ int btf_create(const btf_config* c, btf_engine** out) {
     Scalars h;
     memset(&h, 0, sizeof(h));
     h.nu2 = 1.0; h.sigma2 = 1.0; h.lam2 = 1.0; h.lam2_a = 1.0;
-    CK(cudaMemcpy(e->scal, &h, sizeof(h), cudaMemcpyHostToDevice));
+    CK(h2d(e->scal, &h, sizeof(h)));
     // one-time fills so a forgotten set_state cannot divide by zero
     {
         std::vector<double> ones(tn, 1.0);
         for (double* p : {e->Tau2, e->Tau2_a, e->Tau2_b, e->Tau2_c})
-            CK(cudaMemcpy(p, ones.data(), tn * sizeof(double), cudaMemcpyHostToDevice));
+            CK(h2d(p, ones.data(), tn * sizeof(double)));
     }
 
     // data
@@ -552,6 +567,7 @@ int btf_set_data_negbin(btf_engine* e, const double* Y, int32_t nreps) {
     if (e->Yraw) { CK(cudaFree(e->Yraw)); e->Yraw = nullptr; }
     CK(cudaMalloc((void**)&e->Yraw, total * sizeof(double)));
     CK(cudaMemcpy(e->Yraw, Y, total * sizeof(double), is_device_ptr(Y) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     if (e->nb_work) { CK(cudaFree(e->nb_work)); e->nb_work = nullptr; }
     const size_t rsize = (size_t)e->Rn * e->Rm * e->Rt;
     CK(dev_alloc(&e->nb_work, 8 * rsize + 64));
@@ -626,7 +642,7 @@ int btf_set_state(btf_engine* e, const char* name, const double* host, size_t n)
         // on exactly the random stream it would have continued with
         if (n != 1 || !(host[0] >= 0.0) || host[0] > 9007199254740992.0) return set_err(BTF_EINVAL, "sweep: one non-negative integer below 2^53");
         const unsigned long long v = (unsigned long long)host[0];
-        CK(cudaMemcpy(&e->scal->sweep, &v, sizeof(v), cudaMemcpyHostToDevice));
+        CK(h2d(&e->scal->sweep, &v, sizeof(v)));
         e->resid_valid = false;
         return BTF_OK;
     }
@@ -637,7 +653,7 @@ int btf_set_state(btf_engine* e, const char* name, const double* host, size_t n)
     StateRef r;
     if (!state_ref(e, nm, &r)) return set_err(BTF_EINVAL, "unknown state '%s'", name);
     if (n != r.n) return set_err(BTF_EINVAL, "%s: expected %zu values, got %zu", name, r.n, n);
-    CK(cudaMemcpy(r.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d(r.p, host, n * sizeof(double)));
     if (nm == "W" || nm == "V") e->resid_valid = false;
     // restoring a checkpoint: the residual sum that belongs to the (W, V) just set, so that the next nu2 step uses the same
     // number the interrupted chain would have used (set it AFTER W and V)
@@ -693,7 +709,7 @@ int btf_inject_noise(btf_engine* e, const char* name, const double* host, size_t
     if (b.p && b.n != n) { cudaFree(b.p); b.p = nullptr; }
     if (!b.p) { CK(cudaMalloc((void**)&b.p, n * sizeof(double))); b.n = n; }
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(b.p, host, n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h2d(b.p, host, n * sizeof(double)));
     return BTF_OK;
 }
 
@@ -959,7 +975,7 @@ static int ensure_i8(btf_engine* e) {
         StatsI8Sizes z;
         stats_i8_sizes(e->K, e->nloc_pad, e->Ppad, e->nloc, e->P, e->Nall_pad, e->Ploc, &z);
         CK(cudaMalloc((void**)&e->i8.planes, z.planes_bytes));
-        CK(cudaMemset(e->i8.planes, 0, z.planes_bytes));
+        CK(cudaMemsetAsync(e->i8.planes, 0, z.planes_bytes, st));
         CK(dev_alloc(&e->i8.colmax, (size_t)z.L));
         CK(dev_alloc(&e->i8.expo, (size_t)z.L));
         CK(dev_alloc(&e->i8.D, z.d_elems, false));
@@ -1003,7 +1019,7 @@ static int ensure_i8(btf_engine* e) {
             cudaMemGetInfo(&free_b, &total_b);
             double fits = need <= free_b / 4 ? 1.0 : 0.0, *dflag = nullptr;
             CK(cudaMalloc((void**)&dflag, 8));
-            CK(cudaMemcpy(dflag, &fits, 8, cudaMemcpyHostToDevice));
+            CK(h2d(dflag, &fits, 8));
             if (nccl_allreduce_sum(e->shard, dflag, 1, st)) { cudaFree(dflag); return set_err(BTF_ENCCL, "all-reduce failed: %s", nccl_shard_error()); }
             CK(cudaMemcpyAsync(&fits, dflag, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1490,7 +1506,7 @@ int btf_mu_stats_track(btf_engine* e, int32_t track) {
     const size_t n = (size_t)e->nloc * e->P;
     if (track) {
         if (!e->mu_mean) { CK(dev_alloc(&e->mu_mean, n)); CK(dev_alloc(&e->mu_m2, n)); }
-        else { CK(cudaMemset(e->mu_mean, 0, n * 8)); CK(cudaMemset(e->mu_m2, 0, n * 8)); }
+        else { CK(cudaMemsetAsync(e->mu_mean, 0, n * 8, e->stream)); CK(cudaMemsetAsync(e->mu_m2, 0, n * 8, e->stream)); }
         e->mu_count = 0;
     }
     e->mu_track = track != 0;
@@ -1557,6 +1573,7 @@ int btf_eval_set(btf_engine* e, int32_t slot, const double* target, const uint8_
     CK(dev_alloc(&s.target, n, false));
     CK(cudaMemcpy(s.target, target, n * 8, cudaMemcpyDefault));
     if (cls) { CK(dev_alloc(&s.cls, n, false)); CK(cudaMemcpy(s.cls, cls, n, cudaMemcpyDefault)); }
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     if (cell_state) {
         CK(dev_alloc(&s.mean, n)); CK(dev_alloc(&s.below, n, false)); CK(dev_alloc(&s.above, n, false));
         CK(dev_alloc(&s.c_lt, n)); CK(dev_alloc(&s.c_le, n));
@@ -1688,7 +1705,7 @@ int btf_init_state(btf_engine* e, int32_t init_mask) {
             double z = std::sqrt(-2.0 * std::log(u01())) * std::cos(6.283185307179586 * u01());
             r[i] = std::exp(c.rstdev * z) + 1.0;
         }
-        CK(cudaMemcpy(e->Rdisp, r.data(), rn * sizeof(double), cudaMemcpyHostToDevice));
+        CK(h2d(e->Rdisp, r.data(), rn * sizeof(double)));
     }
     CK(cudaStreamSynchronize(st));
     e->resid_valid = false;
@@ -1701,8 +1718,8 @@ int btf_pg_sample(int32_t device, const double* b, const double* z, double* out,
     CK(cudaSetDevice(device));
     double *db = nullptr, *dz = nullptr, *dout = nullptr;
     CK(cudaMalloc((void**)&db, n * 8)); CK(cudaMalloc((void**)&dz, n * 8)); CK(cudaMalloc((void**)&dout, n * 8));
-    CK(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dz, z, n * 8, cudaMemcpyHostToDevice));
+    CK(h2d(db, b, n * 8));
+    CK(h2d(dz, z, n * 8));
     launch_pg_sample(db, dz, dout, n, seed, 1ull, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "kernels.h"
 
 namespace btf {
@@ -118,11 +119,17 @@ struct G2Args {
     // element-wise guard (stats_i8.cu): rows whose diagonal entries cannot be guaranteed to `tol` relative are flagged
     const unsigned* cntsum; unsigned char* flags; double tol;
     unsigned long long diag_mask[16];   // per column tile: bit q set when product column nt * 36 + q is a diagonal (k, k)
+    // split-K mode (few tiles: narrow shards): nsplit > 1 jobs per tile, each over chunks_per_split K chunks; the exact int32
+    // partial sums are added into D[i8_plane_row][m] with integer atomics (order independent) and recombined by i8_combine
+    int nsplit, chunks_per_split;
+    int32_t* D; long long ldd;
 };
 
 template <int G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant__ CUtensorMap tm_dig, G2Args p) {
+    const CUtensorMap* tm_cnt_p = &tm_cnt;     // counts
+    const CUtensorMap* tm_dig_p = &tm_dig;     // digit planes
     extern __shared__ uint8_t smraw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + G2_STAGES * G2_STAGE_BYTES);   // [STAGES]  TMA -> MMA      (leader's copy is used)
@@ -134,7 +141,8 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int ntiles = p.m_tiles * p.n_tiles;
+    const int ntiles = p.m_tiles * p.n_tiles * p.nsplit;       // jobs: (tile, K split), tile index fastest
+    const int tiles_only = p.m_tiles * p.n_tiles;
 
     if (tid == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { g2_mbar_init(full + s, 1); g2_mbar_init(empty + s, 1); }
@@ -154,17 +162,21 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer (one lane): this CTA's half of the pair's operands
         if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(tm_cnt_p)) : "memory");
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(tm_dig_p)) : "memory");
             int stage = 0; uint32_t phase = 0;
             for (int t = pair; t < ntiles; t += npairs) {
-                const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+                const int sp = t / tiles_only, tt = t - sp * tiles_only;
+                const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
                 const int row_c = mt * 256 + (int)rank * G2_ROWS;                       // count rows of this CTA
                 const int row_d = nt * (G2_CPT * G2_NP) + (int)rank * G2_ROWS;          // digit rows (N half) of this CTA
-                for (int c = 0; c < p.k_chunks; ++c) {
+                const int c_lo = sp * p.chunks_per_split, c_hi = min(p.k_chunks, c_lo + p.chunks_per_split);
+                for (int c = c_lo; c < c_hi; ++c) {
                     g2_mbar_wait(empty + stage, phase ^ 1u);                            // (a fresh barrier passes parity 1)
                     if (rank == 0) g2_expect_tx(full + stage, 2u * G2_STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
                     uint8_t* sa = sm + stage * G2_STAGE_BYTES;
-                    g2_tma_load(&tm_cnt, full + stage, sa, c * G2_BK, row_c);
-                    g2_tma_load(&tm_dig, full + stage, sa + G2_TILE_BYTES, c * G2_BK, row_d);
+                    g2_tma_load(tm_cnt_p, full + stage, sa, c * G2_BK, row_c);
+                    g2_tma_load(tm_dig_p, full + stage, sa + G2_TILE_BYTES, c * G2_BK, row_d);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -178,13 +190,15 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
                 g2_mbar_wait(tempty + acc, acc_phase ^ 1u);                             // both CTAs' epilogues have drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-                for (int c = 0; c < p.k_chunks; ++c) {
+                const int sp = t / tiles_only;
+                const int c_lo = sp * p.chunks_per_split, c_hi = min(p.k_chunks, c_lo + p.chunks_per_split);
+                for (int c = c_lo; c < c_hi; ++c) {
                     g2_mbar_wait(full + stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t a0 = s_u32(sm + stage * G2_STAGE_BYTES), b0 = a0 + G2_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < G2_BK / 32; ++k)
-                        g2_mma(tmem_d, g2_desc(a0 + 32 * k), g2_desc(b0 + 32 * k), (c > 0 || k > 0) ? 1u : 0u);
+                        g2_mma(tmem_d, g2_desc(a0 + 32 * k), g2_desc(b0 + 32 * k), (c > c_lo || k > 0) ? 1u : 0u);
                     g2_commit_pair(empty + stage);                                      // frees the stage in both CTAs
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -197,10 +211,35 @@ i8gemm2_kernel(const __grid_constant__ CUtensorMap tm_cnt, const __grid_constant
         const int quarter = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = pair; t < ntiles; t += npairs) {
-            const int mt = t / p.n_tiles, nt = t - mt * p.n_tiles;
+            const int tt = t % tiles_only;
+            const int mt = tt / p.n_tiles, nt = tt - mt * p.n_tiles;
             g2_mbar_wait(tfull + acc, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int row = mt * 256 + (int)rank * G2_ROWS + quarter * 32 + lane;
+            if (p.nsplit > 1) {
+                // split-K: raw int32 partial sums, integer atomics (the 32 lanes of a warp are 32 consecutive count rows)
+                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+                for (int n = 0; n < G2_CPT * G2_NP; n += 4) {
+                    uint32_t v0, v1, v2, v3;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                                 : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                 : "r"(tb + (uint32_t)n));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    if (row < p.M) {
+                        int32_t* d = p.D + (long long)(nt * (G2_CPT * G2_NP) + n) * p.ldd + row;
+                        if (v0) atomicAdd(d, (int)v0);
+                        if (v1) atomicAdd(d + p.ldd, (int)v1);
+                        if (v2) atomicAdd(d + 2 * p.ldd, (int)v2);
+                        if (v3) atomicAdd(d + 3 * p.ldd, (int)v3);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) g2_arrive_cluster(tempty + acc, 0u);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                continue;
+            }
             const unsigned long long dmask = p.cntsum ? p.diag_mask[nt] : 0ull;
             const double n_half = (dmask && row < p.M) ? 0.5 * (double)p.cntsum[row] : 0.0;     // error bound = n_m 2^(e_c - 55)
             bool bad = false;
@@ -299,12 +338,24 @@ bool make_map(CUtensorMap* tm, const void* base, long long rows, long long ld, l
 // out[m][c] (c < L) for counts [M][ldc] and tile-major digit planes [n_tiles * 252][ldp], contraction length K (multiple
 // of 128).  Returns 0 on success, 1 when this kernel does not apply (too few tiles to fill the pairs, alignment, no TMA
 // entry point: the caller takes the split-K route through the int32 planes), > 1 on a launch error.
+// D / ldd (optional): int32 planes [i8_plane_rows(L)][ldd] for the split-K mode.  Returns 0: `out` written (fused epilogue);
+// 5: split-K, the exact partial sums are in D (the caller recombines); 1: not applicable; > 1 and != 5: launch error.
 int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K, const int* expo,
-                   double* out, long long ldo, int min_tiles, const I8Guard* guard, cudaStream_t st) {
+                   double* out, long long ldo, int min_tiles, const I8Guard* guard, int32_t* D, long long ldd, cudaStream_t st) {
     if (K % G2_BK != 0 || (ldc % 16) || (ldp % 16) || M < 1 || L < 1) return 1;
     if ((reinterpret_cast<uintptr_t>(Cn) & 15) || (reinterpret_cast<uintptr_t>(Pl) & 15)) return 1;
     const int mt = (M + 255) / 256, nt = (L + G2_CPT - 1) / G2_CPT;
-    if (mt * nt < min_tiles) return 1;
+    int nsplit = 1;
+    if (mt * nt < min_tiles) {
+        // few tiles: split the contraction so that the jobs fill the CTA pairs (at least 8 chunks per job)
+        if (!D || min_tiles >= (1 << 29)) return 1;
+        const int kc = K / G2_BK;
+        int dev = 0, nsm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        nsplit = std::min(std::max(1, kc / 8), (nsm / 2) / (mt * nt));       // one wave of jobs on the CTA pairs
+        if (nsplit < 2) return 1;
+    }
     static int sms = 0;
     static bool attr_ok = false;
     if (!attr_ok) {
@@ -319,19 +370,27 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
         attr_ok = true;
     }
     static const bool four = getenv("BTF_I8_G2_STAGES") != nullptr && getenv("BTF_I8_G2_STAGES")[0] == '4';
-    CUtensorMap tc, td;
-    if (!make_map(&tc, Cn, M, ldc, K) || !make_map(&td, Pl, (long long)nt * G2_CPT * G2_NP, ldp, K)) return 1;
     if (nt > 16) return 1;
+    // the descriptors travel as kernel parameters (a CUDA graph keeps its own copy of them)
+    alignas(64) CUtensorMap tm_cnt, tm_dig;
+    if (!make_map(&tm_cnt, Cn, M, ldc, K) || !make_map(&tm_dig, Pl, (long long)nt * G2_CPT * G2_NP, ldp, K)) return 1;
     G2Args p{};
     p.M = M; p.L = L; p.k_chunks = K / G2_BK; p.m_tiles = mt; p.n_tiles = nt; p.expo = expo; p.out = out; p.ldo = ldo;
-    if (guard) {
+    p.chunks_per_split = (p.k_chunks + nsplit - 1) / nsplit;
+    p.nsplit = (p.k_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+    p.D = D; p.ldd = ldd;
+    if (p.nsplit > 1 &&
+        cudaMemset2DAsync(D, (size_t)ldd * sizeof(int32_t), 0, (size_t)M * sizeof(int32_t), (size_t)nt * G2_CPT * G2_NP, st) != cudaSuccess)
+        return 2;
+    if (guard && p.nsplit == 1) {
         p.cntsum = guard->cntsum; p.flags = guard->flags; p.tol = guard->tol;
         for (int k = 0; k * (k + 3) / 2 < L; ++k) { const int c = k * (k + 3) / 2; p.diag_mask[c / G2_CPT] |= 1ull << (c % G2_CPT); }
     }
-    const int pairs = std::min(sms / 2, mt * nt);
-    if (four) i8gemm2_kernel<4><<<2 * pairs, G2_THREADS, g2_smem(4), st>>>(tc, td, p);
-    else i8gemm2_kernel<6><<<2 * pairs, G2_THREADS, g2_smem(6), st>>>(tc, td, p);
-    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+    const int pairs = std::min(sms / 2, mt * nt * p.nsplit);
+    if (four) i8gemm2_kernel<4><<<2 * pairs, G2_THREADS, g2_smem(4), st>>>(tm_cnt, tm_dig, p);
+    else i8gemm2_kernel<6><<<2 * pairs, G2_THREADS, g2_smem(6), st>>>(tm_cnt, tm_dig, p);
+    if (cudaGetLastError() != cudaSuccess) return 2;
+    return p.nsplit > 1 ? 5 : 0;
 }
 
 }  // namespace btf

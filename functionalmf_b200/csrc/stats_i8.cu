@@ -24,7 +24,8 @@ namespace btf {
 int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
                   long long ldd, cudaStream_t st);
 int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, long long ldp, int L, int K, const int* expo,
-                   double* out, long long ldo, int min_tiles, const I8Guard* guard, cudaStream_t st);
+                   double* out, long long ldo, int min_tiles, const I8Guard* guard, int32_t* D, long long ldd,
+                   cudaStream_t st);
 
 namespace {
 
@@ -438,9 +439,12 @@ int stats_i8_product(const StatsI8Buffers& w, int K, const uint8_t* B, long long
     // BTF_I8_GEMM2 = 0: never the 2-CTA kernel; = 1: always (tests); default: when its 256 x 256 tiles fill most CTA pairs
     static const char* g2 = getenv("BTF_I8_GEMM2");
     const int min_tiles = g2 ? (g2[0] == '0' ? (1 << 30) : 0) : 48;
+    // BTF_I8_G2_SPLITK=0: few-tile shapes take the round-1 kernel instead of the split-K mode of the 2-CTA kernel
+    static const bool g2split = !(getenv("BTF_I8_G2_SPLITK") != nullptr && getenv("BTF_I8_G2_SPLITK")[0] == '0');
     const int rc = launch_i8gemm2(reinterpret_cast<const int8_t*>(B), ldb, m_valid, w.planes, kdim_pad, L, kdim_pad, w.expo, out,
-                                  L + K, min_tiles, guard, st);
+                                  L + K, min_tiles, guard, g2split ? w.D + d_off : nullptr, m_pad, st);
     if (rc == 0) return 10;
+    if (rc == 5) return 0;          // exact int32 partial sums in w.D: the recombination kernel finishes (and applies the guard)
     if (rc > 1) return 1;
     // few tiles (small tensors, narrow shards): 128 x 256 tiles with split-K and integer atomics through the int32 planes
     // (the recombination kernel applies the guard on this route)

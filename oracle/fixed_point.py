@@ -1,6 +1,6 @@
 """CPU restatement of the exact fixed-point contraction of the integer statistics path.  TEST INFRASTRUCTURE.
 
-The engine (functionalmf_b200/csrc/stats_i8.cu + i8gemm.cu) computes the product block of the
+The engine (functionalmf_b200/csrc/stats_i8.cu + i8gemm2.cu / i8gemm.cu) computes the product block of the
 sufficient statistics
 
     out[m, c] = sum_k cnt[m, k] * Z[k, c],      Z[k, (k1, k2)] = F[k, k1] * F[k, k2]   (k2 <= k1, packed)
@@ -10,8 +10,9 @@ by writing every column of Z as a fixed-point number against a power-of-two colu
 
     e_c = smallest integer with max_k |Z[k, c]| < 2^e_c,     q[k, c] = rint(Z[k, c] * 2^(54 - e_c)),
 
-splitting q into eight signed base-128 digits, contracting the digit planes with the counts in exact
-int32 arithmetic on the int8 tensor cores and recombining them with ONE rounding:
+splitting q into seven signed base-256 digits (round 1: eight base-128 digits; q and therefore the result are the
+same), contracting the digit planes with the counts in exact int32 arithmetic on the int8 tensor cores and
+recombining them with ONE rounding:
 
     out[m, c] = RN( (sum_k cnt[m, k] * q[k, c]) * 2^(e_c - 54) ).
 
@@ -22,8 +23,8 @@ from fractions import Fraction
 import numpy as np
 
 FIXBITS = 54
-NPLANES = 8
-DIGIT_OFFSET = sum(64 * 128 ** s for s in range(NPLANES))      # 0x0081020408102040
+NPLANES = 7
+DIGIT_OFFSET = sum(128 * 256 ** s for s in range(NPLANES))      # 0x0080808080808080
 
 
 def column_exponent(z):
@@ -41,23 +42,27 @@ def quantise(z, e):
 
 
 def digits(q):
-    """the eight signed base-128 digits of q, carry-free as on the device: fields of q + sum_s 64 * 128^s, minus 64"""
+    """the seven signed base-256 digits of q, carry-free as on the device: fields of q + sum_s 128 * 256^s, minus 128"""
     qq = q + DIGIT_OFFSET
-    assert 0 < qq < 128 ** NPLANES
-    return [((qq >> (7 * s)) & 127) - 64 for s in range(NPLANES)]
+    assert 0 < qq < 256 ** NPLANES
+    return [((qq >> (8 * s)) & 255) - 128 for s in range(NPLANES)]
 
 
 def recombine(planes):
-    """two int64 Horner sums (each below 2^53 in magnitude), one rounding: fma(hi, 2^28, lo)"""
-    hi = ((planes[7] * 128 + planes[6]) * 128 + planes[5]) * 128 + planes[4]
-    lo = ((planes[3] * 128 + planes[2]) * 128 + planes[1]) * 128 + planes[0]
-    assert abs(hi) < 2 ** 53 and abs(lo) < 2 ** 53
-    return hi * 2 ** 28 + lo          # exact integer; the device rounds it once when converting
+    """the device's recombination: two int64 Horner sums hi = (D6, D5, D4), lo = (D3..D0), re-split into
+    H = hi 2^5 + (lo >> 27) and the low 27 bits of lo - both exactly representable in a double - and ONE rounding
+    fma(H, 2^27, l27)"""
+    hi = (planes[6] * 256 + planes[5]) * 256 + planes[4]
+    lo = ((planes[3] * 256 + planes[2]) * 256 + planes[1]) * 256 + planes[0]
+    assert abs(hi) < 2 ** 63 and abs(lo) < 2 ** 63
+    H, l27 = hi * 32 + (lo >> 27), lo & (2 ** 27 - 1)          # (Python's >> floors like the device's arithmetic shift)
+    assert abs(H) < 2 ** 53 and 0 <= l27 < 2 ** 27
+    return H * 2 ** 27 + l27          # exact integer (= hi 2^32 + lo); the device rounds it once when converting
 
 
 def product_block(F, counts, check_digits=False):
     """counts [m, k] (non-negative integers), F [k, K]  ->  out [m, L] float64, L = K (K + 1) / 2 packed (k1 >= k2).
-    check_digits: also go through the eight digit planes and their recombination (slow; the CPU test does)."""
+    check_digits: also go through the seven digit planes and their recombination (slow; the CPU test does)."""
     F = np.asarray(F, dtype=np.float64)
     counts = np.asarray(counts)
     K = F.shape[1]
@@ -78,6 +83,30 @@ def product_block(F, counts, check_digits=False):
                 # then an exact power-of-two scaling
                 out[m, c] = float(np.ldexp(np.float64(float(tot)), e - FIXBITS))
             c += 1
+    return out
+
+
+def product_block_fast(F, counts):
+    """The same definition as product_block for large shapes: q is split as qh 2^27 + ql, the two integer contractions are
+    done by float64 BLAS (every partial sum stays far below 2^53, so they are exact), recombined as Python integers and
+    rounded once.  tests/test_fixed_point_oracle.py checks it against product_block."""
+    F = np.asarray(F, dtype=np.float64)
+    cf = np.asarray(counts, dtype=np.float64)
+    assert cf.sum(axis=1).max() < 2 ** 24
+    K = F.shape[1]
+    il = np.tril_indices(K)
+    Z = F[:, il[0]] * F[:, il[1]]
+    mx = np.abs(Z).max(axis=0)
+    e = np.where(mx > 0, np.frexp(np.where(mx > 0, mx, 1.0))[1], 0).astype(np.int64)
+    q = np.rint(np.ldexp(Z, (FIXBITS - e)[None, :].astype(np.int32))).astype(np.int64)
+    qh, ql = q >> 27, q & (2 ** 27 - 1)
+    Sh = (cf @ qh.astype(np.float64)).astype(np.int64)
+    Sl = (cf @ ql.astype(np.float64)).astype(np.int64)
+    out = np.empty(Sh.shape)
+    for m in range(Sh.shape[0]):
+        for c in range(Sh.shape[1]):
+            tot = int(Sh[m, c]) * 2 ** 27 + int(Sl[m, c])
+            out[m, c] = float(np.ldexp(np.float64(float(tot)), int(e[c]) - FIXBITS))
     return out
 
 

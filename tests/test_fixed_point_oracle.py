@@ -10,10 +10,10 @@ from oracle import fixed_point as FP
 
 def test_digits_round_trip_and_range():
     rs = np.random.RandomState(0)
-    for q in [0, 1, -1, 2 ** 54, -2 ** 54, 63, 64, -64, -65] + [int(v) for v in rs.randint(-2 ** 62, 2 ** 62, size=2000) >> 8]:
+    for q in [0, 1, -1, 2 ** 54, -2 ** 54, 127, 128, -128, -129] + [int(v) for v in rs.randint(-2 ** 62, 2 ** 62, size=2000) >> 8]:
         d = FP.digits(q)
-        assert all(-64 <= x <= 63 for x in d)
-        assert sum(x * 128 ** s for s, x in enumerate(d)) == q
+        assert len(d) == 7 and all(-128 <= x <= 127 for x in d)
+        assert sum(x * 256 ** s for s, x in enumerate(d)) == q
 
 
 def test_column_exponent_is_tight():
@@ -48,3 +48,10 @@ def test_product_block_error_bound(K, n, R):
     # and it agrees with the plain float64 contraction to accumulation noise
     np.testing.assert_allclose(got, naive, rtol=0, atol=1e-13 * np.abs(naive).max())
     assert len(exact) == counts.shape[0]
+
+
+def test_fast_product_block_equals_the_definition():
+    rs = np.random.RandomState(5)
+    F = rs.normal(size=(90, 5)) * np.exp(2 * rs.normal(size=(1, 5)))
+    counts = rs.randint(0, 4, size=(7, 90))
+    assert np.array_equal(FP.product_block_fast(F, counts), FP.product_block(F, counts))

@@ -136,6 +136,31 @@ def test_sweep_matches_the_fp64_path(shape, gemm_mode):
     assert a['nu2'] == pytest.approx(b['nu2'], rel=1e-9) and a['sigma2'] == pytest.approx(b['sigma2'], rel=1e-9)
 
 
+def test_two_cta_gemm_split_k_and_fused_modes_are_exact():
+    """300 rows x (64 x 128) columns at K = 16: the row contraction has 2 x 4 tiles of the 2-CTA GEMM, so it runs in its
+    split-K mode (int32 atomics + recombination kernel); the column contraction has 128 tiles and runs with the fused
+    epilogue.  Both must equal the fixed-point definition bit for bit (oracle.fixed_point.product_block_fast)."""
+    from oracle.fixed_point import product_block_fast
+    from functionalmf_b200 import _lib as L
+    N, M, T, R, K = 300, 64, 128, 2, 16
+    rs, W, V, Y = _problem(N, M, T, R, K, 31)
+    eng = _engine(N, M, T, R, K, 'BTF_STATS_FORCE_I8')
+    try:
+        eng.set_data_gaussian(Y)
+        _load(eng, rs, W, V)
+        eng.enable_diag(True)
+        eng.set_sample_mask(L.SAMPLE_W | L.SAMPLE_V)
+        eng.inject('z_W', np.zeros(N * K))
+        eng.sweep(1)
+        Lp = K * (K + 1) // 2
+        cnt = (~np.isnan(Y)).sum(axis=-1).reshape(N, M * T)
+        np.testing.assert_array_equal(eng.diag('row_stats')[:, :Lp], product_block_fast((V * 1.1).reshape(M * T, K), cnt))
+        np.testing.assert_array_equal(eng.diag('col_stats')[:, :Lp], product_block_fast(eng.get('W'), cnt.T))
+    finally:
+        eng.close()
+        os.environ.pop('BTF_STATS_FORCE_I8', None)
+
+
 def _exact_product_block(F, cnt):
     """sum_k cnt[m,k] F[k,k1] F[k,k2] in extended precision (packed lower triangle), as float64."""
     K = F.shape[1]
