@@ -386,7 +386,10 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
         p.cntsum = guard->cntsum; p.flags = guard->flags; p.tol = guard->tol;
         for (int k = 0; k * (k + 3) / 2 < L; ++k) { const int c = k * (k + 3) / 2; p.diag_mask[c / G2_CPT] |= 1ull << (c % G2_CPT); }
     }
-    const int pairs = std::min(sms / 2, mt * nt * p.nsplit);
+    // BTF_I8_G2_PAIRS=n: at most n CTA pairs, so that the rest of the SMs stay free for the linear block on the other stream
+    static const int pair_cap = getenv("BTF_I8_G2_PAIRS") ? atoi(getenv("BTF_I8_G2_PAIRS")) : 0;
+    int pairs = std::min(sms / 2, mt * nt * p.nsplit);
+    if (pair_cap > 0 && p.nsplit == 1) pairs = std::min(pairs, pair_cap);
     if (four) i8gemm2_kernel<4><<<2 * pairs, G2_THREADS, g2_smem(4), st>>>(tm_cnt, tm_dig, p);
     else i8gemm2_kernel<6><<<2 * pairs, G2_THREADS, g2_smem(6), st>>>(tm_cnt, tm_dig, p);
     if (cudaGetLastError() != cudaSuccess) return 2;

@@ -464,7 +464,9 @@ int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S,
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
     // split-K partials are summed in split order by the recombination kernel
     int nsplit = 1;
-    const int target = resident ? 8 * sms : 2 * sms;          // resident: 8 items per CTA; classic: one wave of two CTAs per SM
+    // BTF_SF_WAVES=w: w times as many (smaller) items, for the block scheduler to balance when the GEMM holds part of the SMs
+    static const int waves = getenv("BTF_SF_WAVES") ? std::max(1, atoi(getenv("BTF_SF_WAVES"))) : 1;
+    const int target = resident ? 8 * sms : 2 * sms * waves;  // resident: 8 items per CTA; classic: one wave of two CTAs per SM
     if (m_tiles < target) {
         nsplit = target / m_tiles;       // never a partial last wave
         if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
