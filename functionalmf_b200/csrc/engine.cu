@@ -5,6 +5,7 @@
 #include "nccl_shard.h"
 
 #include <nvtx3/nvToolsExt.h>
+#include <sched.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -13,6 +14,7 @@
 #include <cstdlib>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace btf;
@@ -81,6 +83,8 @@ struct btf_engine {
     double* staging[2] = {nullptr, nullptr};   // upload staging (kept for the engine's lifetime: no malloc/free per call, no leak on error paths)
     size_t staging_bytes = 0;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr};
+    double* hstage[2] = {nullptr, nullptr};    // pinned bounce buffers for uploads from ordinary (pageable) host memory
+    size_t hstage_bytes = 0;
     // NB dispersion
     double* Rdisp = nullptr; int Rn = 1, Rm = 1, Rt = 1; double* nb_work = nullptr;
     double* nb_hist = nullptr; int nb_hist_stride = 0;   // count histograms per R group (integer counts)
@@ -421,6 +425,7 @@ void btf_destroy(btf_engine* e) {
     for (int i = 0; i < 6; ++i) if (e->i8_ev[i / 3][i % 3]) cudaEventDestroy(e->i8_ev[i / 3][i % 3]);
     for (int i = 0; i < 2; ++i) {
         if (e->staging[i]) cudaFree(e->staging[i]);
+        if (e->hstage[i]) cudaFreeHost(e->hstage[i]);
         if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]);
         if (e->ev_k0[i]) cudaEventDestroy(e->ev_k0[i]);
         if (e->side[i]) cudaStreamDestroy(e->side[i]);
@@ -455,6 +460,35 @@ static int upload_rows(btf_engine* e, const double* src, size_t row_elems, int r
     return BTF_OK;
 }
 
+// Is `p` ordinary host memory (neither page-locked by CUDA nor device / managed memory)?
+static bool is_pageable_host_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy with several host threads: one thread copies ~10 GB/s, which is also all a cudaMemcpy from pageable memory
+// reaches (it goes through the driver's own single-threaded bounce buffer)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    // threads: the cores this process may run on, at most 16 (C2 on the bench box: 8 threads 36.6 GB/s, 16 threads 40.6 GB/s,
+    // pinned source 55 GB/s), and at least 4 MB each
+    unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hw = (unsigned)CPU_COUNT(&cs);
+    int nt = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 4, 16), std::max<size_t>(1, bytes >> 22));
+    if (const char* s = getenv("BTF_UPLOAD_THREADS")) nt = std::max(1, atoi(s));
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    for (int i = 0; i < nt; ++i) {
+        const size_t o = (size_t)i * per;
+        if (o >= bytes) break;
+        const size_t n = std::min(per, bytes - o);
+        th.emplace_back([=]() { memcpy((char*)dst + o, (const char*)src + o, n); });
+    }
+    for (auto& t : th) t.join();
+}
+
 // Pre-reduce `nrows` local rows starting at local row `row0` (streaming form for shards that
 // are generated or loaded piecewise; reset != 0 clears the running totals first).
 int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int32_t nrows, int32_t nreps,
@@ -470,11 +504,22 @@ int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int
     const size_t row_elems = (size_t)e->P * nreps;
     if (reset) CK(cudaMemsetAsync(&e->scal->ss_total, 0, 2 * sizeof(double), e->stream));   // ss_total, n_obs
     const bool on_dev = is_device_ptr(Y);
+    // Ordinary numpy memory: a cudaMemcpy from it runs at ~10 GB/s, and page-locking it in place for one upload costs
+    // more than that copy (cudaHostRegister ~5-8 GB/s; tools/upload_timing.py) - so it is copied by several host threads
+    // into two pinned bounce buffers, from which the asynchronous copies run at link speed.  BTF_UPLOAD_BOUNCE=0: plain copy.
+    const bool bounce = !on_dev && is_pageable_host_ptr(Y) && !(getenv("BTF_UPLOAD_BOUNCE") && getenv("BTF_UPLOAD_BOUNCE")[0] == '0');
     int chunk = nrows;
     if (!on_dev) {
         // two staging buffers: the copy of piece i + 1 (copy stream) runs under the pre-reduction of piece i
-        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nrows, 1), ((size_t)256 << 20) / (row_elems * 8)));
+        const size_t piece_bytes = bounce ? ((size_t)64 << 20) : ((size_t)256 << 20);
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nrows, 1), piece_bytes / (row_elems * 8)));
         const size_t need = (size_t)chunk * row_elems * sizeof(double);
+        if (bounce && need > e->hstage_bytes) {
+            for (int b = 0; b < 2; ++b) { if (e->hstage[b]) cudaFreeHost(e->hstage[b]); e->hstage[b] = nullptr; }
+            e->hstage_bytes = 0;
+            for (int b = 0; b < 2; ++b) CK(cudaMallocHost((void**)&e->hstage[b], need));
+            e->hstage_bytes = need;
+        }
         if (need > e->staging_bytes) {
             for (int b = 0; b < 2; ++b) { if (e->staging[b]) cudaFree(e->staging[b]); e->staging[b] = nullptr; }
             e->staging_bytes = 0;
@@ -493,8 +538,14 @@ int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int
         const int b = piece & 1;
         const double* src = on_dev ? Y + (size_t)r0 * row_elems : e->staging[b];
         if (!on_dev) {
+            const double* hsrc = Y + (size_t)r0 * row_elems;
+            if (bounce) {
+                if (piece >= 2) CK(cudaEventSynchronize(e->ev_h2d[b]));                    // the bounce buffer's previous copy has left it
+                parallel_memcpy(e->hstage[b], hsrc, (size_t)rows * row_elems * sizeof(double));
+                hsrc = e->hstage[b];
+            }
             if (piece >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->ev_k0[b], 0));       // the buffer's previous pre-reduction is done
-            CK(cudaMemcpyAsync(e->staging[b], Y + (size_t)r0 * row_elems, (size_t)rows * row_elems * sizeof(double),
+            CK(cudaMemcpyAsync(e->staging[b], hsrc, (size_t)rows * row_elems * sizeof(double),
                                cudaMemcpyHostToDevice, e->copy_stream));
             CK(cudaEventRecord(e->ev_h2d[b], e->copy_stream));
             CK(cudaStreamWaitEvent(e->stream, e->ev_h2d[b], 0));
