@@ -707,11 +707,8 @@ static void launch_lookahead_t(const BandSolveArgs& a, cudaStream_t st) {
     using G = LaGeom<KB, Q>;
     const size_t smem = G::smem_doubles(a.T, a.RD) * sizeof(double);
     auto kern = band_lookahead_kernel<KB, Q>;
-    static size_t max_set = 0;
-    if (smem > 48 * 1024 && smem > max_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        max_set = smem;
-    }
+    static PerDeviceMax max_set;
+    if (smem > 48 * 1024 && max_set.raise(smem)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<a.ncols_loc, G::NT, smem, st>>>(a);
 }
 

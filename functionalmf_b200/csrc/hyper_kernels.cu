@@ -75,11 +75,8 @@ void launch_tau2(const HyperArgs& a, cudaStream_t st) {
     if (ncol <= 0) return;
     if (a.Tau2_a) {   // Tau2_a == nullptr: only the lam2 partials are wanted (Tau2 held fixed)
         size_t smem = (size_t)a.T * a.K * sizeof(double);
-        static size_t max_set = 0;
-        if (smem > 48 * 1024 && smem > max_set) {
-            cudaFuncSetAttribute(tau2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            max_set = smem;
-        }
+        static PerDeviceMax max_set;
+        if (smem > 48 * 1024 && max_set.raise(smem)) cudaFuncSetAttribute(tau2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tau2_kernel<<<ncol, 128, smem, st>>>(a);
     }
     if (a.lam_partials) lam_partial_kernel<<<ncol, 128, 0, st>>>(a);

@@ -220,12 +220,11 @@ __global__ void __launch_bounds__(160, STAGES > 2 ? 1 : 2) i8gemm_kernel(I8Args 
 int launch_i8gemm(const int8_t* A, long long lda, int M, const int8_t* B, long long ldb, int N, int K, int32_t* D,
                   long long ldd, cudaStream_t st) {
     if (K % I8_BK != 0 || (lda % 16) || (ldb % 16) || (ldd % 4)) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         if (cudaFuncSetAttribute(i8gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return 2;
         if (cudaFuncSetAttribute(i8gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM2) != cudaSuccess) return 2;
         if (cudaFuncSetAttribute(i8gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM3) != cudaSuccess) return 2;
-        attr_set = true;
     }
     const int mt = (M + I8_BM - 1) / I8_BM, nt = (N + I8_BN - 1) / I8_BN, nchunks = K / I8_BK;
     // split-K when the tiles alone cannot fill the GPU (few rows: multi-GPU shards, small tensors)

@@ -356,18 +356,15 @@ int launch_i8gemm2(const int8_t* Cn, long long ldc, int M, const int8_t* Pl, lon
         nsplit = std::min(std::max(1, kc / 8), (nsm / 2) / (mt * nt));       // one wave of jobs on the CTA pairs
         if (nsplit < 2) return 1;
     }
-    static int sms = 0;
-    static bool attr_ok = false;
-    if (!attr_ok) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         if (cudaFuncSetAttribute(i8gemm2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem(6)) != cudaSuccess ||
             cudaFuncSetAttribute(i8gemm2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem(4)) != cudaSuccess) {
             cudaGetLastError();
             return 1;
         }
-        attr_ok = true;
     }
     static const bool four = getenv("BTF_I8_G2_STAGES") != nullptr && getenv("BTF_I8_G2_STAGES")[0] == '4';
     if (nt > 16) return 1;

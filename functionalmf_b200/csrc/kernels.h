@@ -5,6 +5,30 @@
 #include "common.cuh"
 
 namespace btf {
+// cudaFuncSetAttribute belongs to a device's context: "already done" bookkeeping is kept per device, so that a process
+// that drives several GPUs (or creates engines on different devices one after the other) configures each of them.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long b = 1ull << (d & 63);
+        if (mask & b) return false;
+        mask |= b;
+        return true;
+    }
+};
+struct PerDeviceMax {
+    size_t v[64] = {};
+    bool raise(size_t s) {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (s <= v[d & 63]) return false;
+        v[d & 63] = s;
+        return true;
+    }
+};
+
 
 // ---------------------------------------------------------------- K0 prereduce
 // Y chunk [rows][P][R] (NaN = missing) -> cnt u8, S f64 at pitch `ld`; per-block

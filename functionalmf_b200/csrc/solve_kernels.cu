@@ -402,11 +402,9 @@ void launch_band_solve(const BandSolveArgs& a, cudaStream_t st) {
     int nt2 = (((nco + 3) / 4 + 31) / 32) * 32;
     if (nt2 > nt) nt = nt2;
     size_t smem = ((size_t)kd * (kd + 1) + 4 * (size_t)kd + nco + (size_t)a.T * (q + 1) + a.RD + 8 + 40) * sizeof(double);
-    static size_t max_set = 0;
-    if (smem > 48 * 1024 && smem > max_set) {
+    static PerDeviceMax max_set;
+    if (smem > 48 * 1024 && max_set.raise(smem))
         cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        max_set = smem;
-    }
     band_solve_kernel<<<a.ncols_loc, nt, smem, st>>>(a);
 }
 

@@ -370,8 +370,8 @@ void launch_sf_cfg(const double* S, long long lds, const double* F, int K, int m
                    int nsplit, int grid, double* out, cudaStream_t st) {
     const size_t smem = (size_t)(NST * (TRANS ? KC * 132 : 128 * (KC + 4)) + NST * KC * (KB + 4)) * sizeof(double);
     auto kern = sf_kernel<KB, TRANS, KC, NST, MINB>;
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int cps = (nchunks + nsplit - 1) / nsplit;
     const int nitems = m_tiles * nsplit;
     kern<<<grid > 0 ? std::min(grid, nitems) : nitems, 256, smem, st>>>(S, lds, F, K, m_valid, nchunks, cps, m_tiles, nitems, out);
@@ -423,8 +423,8 @@ void stats_i8_digits(const StatsI8Buffers& w, int K, const double* F, int f_rows
     cudaMemsetAsync(w.colmax, 0, (size_t)L * 8, st);
     zmax_kernel<<<dim3((f_rows + 127) / 128, (L + 255) / 256), 256, (size_t)128 * K * 8, st>>>(F, f_rows, K, L, w.colmax);
     const size_t zs = (size_t)256 * (K + 1) * 8 + (size_t)((L + 3) / 4) * 8;
-    static size_t zs_set = 0;
-    if (zs > 48 * 1024 && zs > zs_set) { cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs); zs_set = zs; }
+    static PerDeviceMax zs_set;
+    if (zs > 48 * 1024 && zs_set.raise(zs)) cudaFuncSetAttribute(zdigits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs);
     // few factor rows (the column side: W has N rows): split the product columns over gridDim.y so the launch fills the GPU
     const int nbx = (kdim_pad + 255) / 256;
     const int nby = std::max(1, std::min((L + 3) / 4, 592 / nbx));
@@ -460,8 +460,8 @@ int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S,
     // BTF_SF_RESIDENT=1: one CTA per SM with a small shared-memory footprint, dealt (tile, split) items round-robin,
     // so that the linear block (HBM) and the int8 GEMM (tensor cores, L2) share every SM when they run on two streams
     static const bool resident = getenv("BTF_SF_RESIDENT") != nullptr && getenv("BTF_SF_RESIDENT")[0] != '0';
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
     // split-K partials are summed in split order by the recombination kernel
     int nsplit = 1;
     // BTF_SF_WAVES=w: w times as many (smaller) items, for the block scheduler to balance when the GEMM holds part of the SMs

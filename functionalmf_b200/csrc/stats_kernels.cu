@@ -569,11 +569,8 @@ static void launch_stats_t(const StatsPlan& p, const void* wt, const double* sv,
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
     auto kern = stats_kernel<BM, WR, WC, CTM, KC, TRANS, WT, KFIX>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     dim3 grid(p.mtiles, p.nsplit);
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
@@ -587,11 +584,8 @@ static void launch_stats_ovl_t(const StatsPlan& p, const void* wt, const double*
     a.nchunks = p.nchunks; a.chunks_per_split = p.chunks_per_split;
     a.m_valid = m_valid; a.out_split_stride = (long long)p.out_elems_per_split;
     auto kern = stats_kernel_ovl<BM, WR, WC, CTM, KC, TRANS, WT, KFIX, UNI, NH>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     dim3 grid(p.mtiles, p.nsplit, NH);
     kern<<<grid, 32 * WR * WC, p.smem_bytes, st>>>(a);
 }
