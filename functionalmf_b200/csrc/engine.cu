@@ -952,7 +952,11 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
             const int max_split = std::max(1, std::min(8, (int)((2ll * e->P) / std::max(e->Ploc, 1))));
             if (e->Ploc > 0) { whole_split = stats_i8_linear(e->i8, true, e->K, e->Scol, e->Ploc_pad, e->W, e->Nall_pad, e->Ploc, max_split, e->i8.bpart, sb); e->launches++; }
         } else if (e->nloc > 0) {
-            stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, Wloc, e->nloc_pad, e->P, 1, e->i8.bpart, sb); e->launches++;
+            // one GPU: the contraction may be split (the partial sums fit in the buffer that also serves the row step);
+            // a row-sharded engine reduce-scatters ONE set of partial sums
+            const size_t cap = std::max((size_t)e->i8.nsplit_b_row * e->nloc * e->K, (size_t)2 * e->P * e->K) / ((size_t)e->P * e->K);
+            const int max_split = e->shard ? 1 : (int)std::min<size_t>(4, std::max<size_t>(cap, 1));
+            whole_split = stats_i8_linear(e->i8, true, e->K, e->S, e->Ppad, Wloc, e->nloc_pad, e->P, max_split, e->i8.bpart, sb); e->launches++;
         } else {
             cudaMemsetAsync(e->i8.bpart, 0, (size_t)e->P * e->K * sizeof(double), sb);
         }
@@ -992,7 +996,7 @@ static int col_step_i8(btf_engine* e, bool fork, int timer, BandFn band) {
             const I8Guard gc{e->cnt_colsum + q0, e->guard_flags + std::max(e->nloc, 1) + q0, e->guard_n + 1, stats_i8_guard_tol()};
             const I8Guard* gp = e->guard_on ? &gc : nullptr;
             if (lin_whole && scol) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, whole_split, q0, e->Ploc, out, gp, st);
-            else if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, 1, (long long)e->p0 + q0, e->P, out, gp, st);
+            else if (lin_whole) stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart, whole_split, (long long)e->p0 + q0, e->P, out, gp, st);
             else stats_i8_combine(e->i8, e->K, np, ldd, q0, product == 10, e->i8.bpart + (size_t)2 * q0 * e->K, lin_split, 0, np, out, gp, st);
             e->launches++;
             if (e->guard_on) {

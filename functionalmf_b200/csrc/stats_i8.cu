@@ -471,6 +471,17 @@ int stats_i8_linear(const StatsI8Buffers& w, bool trans, int K, const double* S,
         nsplit = target / m_tiles;       // never a partial last wave
         if (nsplit > nchunks / 8) nsplit = nchunks / 8 > 0 ? nchunks / 8 : 1;
         if (nsplit > max_split) nsplit = max_split;
+    } else if (max_split > 1 && !resident) {
+        // more tiles than CTA slots: the items run in ceil(items / slots) rounds, and a partial last round idles part of the
+        // GPU (C2 columns: 512 tiles on 296 slots = 2 rounds for 1.73 rounds of work).  Splitting the contraction s ways
+        // makes the rounds s times shorter: pick the s with the least rounds / s, 2 % per extra split for the partial sums.
+        double best = 1e30;
+        for (int s = 1; s <= max_split && s <= std::max(1, nchunks / 8); ++s) {
+            const int cps = (nchunks + s - 1) / s, se = (nchunks + cps - 1) / cps;
+            const long long rounds = ((long long)m_tiles * se + target - 1) / target;
+            const double cost = (double)rounds / se * (1.0 + 0.02 * (se - 1));
+            if (cost < best - 1e-12) { best = cost; nsplit = se; }
+        }
     }
     { const int cps = (nchunks + nsplit - 1) / nsplit; nsplit = (nchunks + cps - 1) / cps; }
     if (K <= 8) { if (trans) launch_sf_t<8, true>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); else launch_sf_t<8, false>(S, lds, F, K, m_valid, m_tiles, nchunks, nsplit, resident, sms, out, st); }
