@@ -77,7 +77,10 @@ const char* btf_last_error(void);
 
 /* ---- data (factor.py:316-330, 437-445, 494-508).  `Y` holds the LOCAL rows
  * [row_end-row_begin, M, T, nreps]; NaN = missing.  Host or device pointers are
- * both accepted (detected with cudaPointerGetAttributes). */
+ * both accepted (detected with cudaPointerGetAttributes).  1 <= nreps <= 255: the
+ * compact form keeps the number of observed replicates of a cell in one byte (the
+ * reference has no such limit; BTF_EINVAL otherwise).  Ordinary (pageable) host memory
+ * is copied through pinned bounce buffers by several host threads. */
 int btf_set_data_gaussian(btf_engine* e, const double* Y, int32_t nreps);
 /* streaming form: rows [row0, row0+nrows) of the local shard; reset != 0 on the first piece */
 int btf_set_data_gaussian_rows(btf_engine* e, const double* Y, int32_t row0, int32_t nrows, int32_t nreps,
